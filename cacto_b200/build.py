@@ -1,0 +1,55 @@
+"""Build libcacto_b200.so in-tree with nvcc for sm_100a (one object per .cu, compiled in parallel)."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, 'csrc')
+OUT = os.path.join(HERE, 'libcacto_b200.so')
+BUILD = os.path.join(ROOT, 'build')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+FLAGS = ['-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
+# bit-exact fp64 files must not contract a*b+c into FMA
+PER_FILE = {'segtree.cu': ['-fmad=false'], 'rtg.cu': ['-fmad=false']}
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')] + [os.path.join(ROOT, 'include', 'cacto_b200.h')]
+    objs, jobs = [], []
+    for f in sources():
+        src, obj = os.path.join(CSRC, f), os.path.join(BUILD, f[:-3] + '.o')
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            jobs.append([NVCC] + ARCH + FLAGS + PER_FILE.get(f, []) + ['-c', src, '-o', obj])
+
+    def run(cmd):
+        if verbose:
+            print(' '.join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
+        return r
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    if force or jobs or _stale(OUT, objs):
+        run([NVCC] + ARCH + ['-shared', '-o', OUT] + objs)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose=True))

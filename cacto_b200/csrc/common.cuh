@@ -1,0 +1,49 @@
+// common.cuh -- launch helpers and shared-memory tile staging used by the element-wise kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "cacto_b200.h"
+
+namespace cacto {
+
+#define CACTO_LAUNCH_CHECK()                         \
+  do {                                               \
+    cudaError_t e__ = cudaGetLastError();            \
+    if (e__ != cudaSuccess) return (int)e__;         \
+  } while (0)
+
+// Padded row stride (odd number of elements) so that "thread r touches row r" is bank-conflict free.
+__host__ __device__ constexpr int pad_odd(int w) { return (w & 1) ? w : w + 1; }
+
+// Rows [row0, row0+rows) of a row-major [B][W] array  <->  a shared tile with stride pad_odd(W).
+// Global accesses are fully coalesced (consecutive threads touch consecutive elements).
+template <int W, int NT, typename T>
+__device__ __forceinline__ void tile_load_rows(const T* __restrict__ g, T* __restrict__ s, int rows) {
+  constexpr int WP = pad_odd(W);
+  for (int i = threadIdx.x; i < rows * W; i += NT) {
+    int r = i / W, c = i - r * W;
+    s[r * WP + c] = g[i];
+  }
+}
+template <int W, int NT, typename T>
+__device__ __forceinline__ void tile_store_rows(T* __restrict__ g, const T* __restrict__ s, int rows) {
+  constexpr int WP = pad_odd(W);
+  for (int i = threadIdx.x; i < rows * W; i += NT) {
+    int r = i / W, c = i - r * W;
+    g[i] = s[r * WP + c];
+  }
+}
+
+// Thread `threadIdx.x` publishes its W register values as row threadIdx.x of the tile, then the CTA
+// writes the tile out coalesced.  All threads of the CTA must call it.
+template <int W, int NT, typename T>
+__device__ __forceinline__ void stage_out_rows(T* __restrict__ g_tile, const T* vals, T* smem, int rows) {
+  constexpr int WP = pad_odd(W);
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < W; ++c) smem[threadIdx.x * WP + c] = vals[c];
+  __syncthreads();
+  tile_store_rows<W, NT, T>(g_tile, smem, rows);
+}
+
+}  // namespace cacto

@@ -1,0 +1,262 @@
+// segtree.cu -- K4: the prioritized-replay sum/min segment trees (segment_tree.py) and the sampled
+// row gather (replay_buffer.py), bit-exact with the reference:
+//   * every internal node is exactly left (+|min) right in fp64 -- the reference's fixed reduction order
+//     (segment_tree.py:76-86) -- so a level-synchronous recomputation of the touched ancestors, after the
+//     leaves are final, gives the same bits as the reference's sequential leaf-by-leaf walks;
+//   * duplicate indices in one batch: the LAST occurrence wins (sequential semantics of
+//     replay_buffer.py:210-216), resolved with an atomicMax stamp;
+//   * all fp64 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction).
+// The trees (2 x 1 MiB at capacity 2^16) are L2-resident; the kernels are latency-bound.
+#include "common.cuh"
+
+namespace cacto {
+
+constexpr int ST_THREADS = 1024;
+
+// Level-synchronous update by ONE CTA.  The top levels (<= 32 nodes) are folded by warp 0 with shuffles.
+__global__ void __launch_bounds__(ST_THREADS) k_segtree_update(double* __restrict__ sum, double* __restrict__ mn, int cap,
+                                                               const int64_t* __restrict__ idx, const double* __restrict__ val,
+                                                               int n, int* __restrict__ stamp) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += ST_THREADS) atomicMax(&stamp[(int)idx[i]], i);
+  __syncthreads();
+  for (int i = tid; i < n; i += ST_THREADS) {
+    const int j = (int)idx[i];
+    if (stamp[j] == i) {
+      if (sum) sum[cap + j] = val[i];
+      if (mn) mn[cap + j] = val[i];
+    }
+  }
+  __syncthreads();
+  // levels whose node count exceeds one warp: recompute every touched ancestor from its (final) children
+  int shift = 1;
+  for (; (cap >> shift) > 32; ++shift) {
+    for (int i = tid; i < n; i += ST_THREADS) {
+      const int node = (cap + (int)idx[i]) >> shift;
+      if (sum) {
+        const double l = sum[2 * node], r = sum[2 * node + 1];
+        sum[node] = __dadd_rn(l, r);
+      }
+      if (mn) {
+        const double a = mn[2 * node], b = mn[2 * node + 1];
+        mn[node] = (b < a) ? b : a;    // Python min(a, b): b only if strictly smaller
+      }
+    }
+    __syncthreads();
+  }
+  // remaining levels: W = cap >> shift (<= 32) nodes [W, 2W) and everything above, by warp 0
+  if (tid < 32) {
+    int W = cap >> shift;
+    double s = 0.0, m = 0.0;
+    if (W >= 1) {
+      if (tid < W) {
+        const int node = W + tid;
+        if (sum) {
+          const double l = sum[2 * node], r = sum[2 * node + 1];
+          s = __dadd_rn(l, r);
+          sum[node] = s;
+        }
+        if (mn) {
+          const double a = mn[2 * node], b = mn[2 * node + 1];
+          m = (b < a) ? b : a;
+          mn[node] = m;
+        }
+      }
+      for (W >>= 1; W >= 1; W >>= 1) {
+        const int src = (2 * tid) & 31;
+        const double l = __shfl_sync(0xffffffffu, s, src), r = __shfl_sync(0xffffffffu, s, src + 1 > 31 ? 31 : src + 1);
+        const double a = __shfl_sync(0xffffffffu, m, src), b = __shfl_sync(0xffffffffu, m, src + 1 > 31 ? 31 : src + 1);
+        if (tid < W) {
+          s = __dadd_rn(l, r);
+          m = (b < a) ? b : a;
+          if (sum) sum[W + tid] = s;
+          if (mn) mn[W + tid] = m;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += ST_THREADS) stamp[(int)idx[i]] = -1;
+}
+
+// segment_tree.py:36-49 -- the recursion fixes the association order of the partial sums.
+__device__ double reduce_sum(const double* v, int start, int end, int node, int lo, int hi) {
+  if (start == lo && end == hi) return v[node];
+  const int mid = (lo + hi) / 2;
+  if (end <= mid) return reduce_sum(v, start, end, 2 * node, lo, mid);
+  if (mid + 1 <= start) return reduce_sum(v, start, end, 2 * node + 1, mid + 1, hi);
+  const double a = reduce_sum(v, start, mid, 2 * node, lo, mid);
+  const double b = reduce_sum(v, mid + 1, end, 2 * node + 1, mid + 1, hi);
+  return __dadd_rn(a, b);
+}
+__device__ double reduce_min(const double* v, int start, int end, int node, int lo, int hi) {
+  if (start == lo && end == hi) return v[node];
+  const int mid = (lo + hi) / 2;
+  if (end <= mid) return reduce_min(v, start, end, 2 * node, lo, mid);
+  if (mid + 1 <= start) return reduce_min(v, start, end, 2 * node + 1, mid + 1, hi);
+  const double a = reduce_min(v, start, mid, 2 * node, lo, mid);
+  const double b = reduce_min(v, mid + 1, end, 2 * node + 1, mid + 1, hi);
+  return (b < a) ? b : a;
+}
+
+__global__ void k_segtree_reduce(const double* __restrict__ sum, const double* __restrict__ mn, int cap, int start, int end_incl,
+                                 double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (sum) out[0] = reduce_sum(sum, start, end_incl, 1, 0, cap - 1);
+    if (mn) out[1] = reduce_min(mn, start, end_incl, 1, 0, cap - 1);
+  }
+}
+
+// replay_buffer.py:139-157 -- stratified proportional sampling.
+__global__ void __launch_bounds__(256) k_segtree_sample(const double* __restrict__ sum, const double* __restrict__ mn, int cap,
+                                                        int max_idx, const double* __restrict__ uniforms, int n,
+                                                        int64_t* __restrict__ idx_out, double* __restrict__ leaf_out,
+                                                        double* __restrict__ totals) {
+  __shared__ double s_total;
+  if (threadIdx.x == 0) {
+    // sum(0, max_idx - 1): python end-exclusive -> inclusive max_idx - 2 (quirk Q4: newest slot excluded)
+    const double pt = reduce_sum(sum, 0, max_idx - 2, 1, 0, cap - 1);
+    s_total = pt;
+    if (blockIdx.x == 0) {
+      totals[0] = pt;
+      totals[1] = sum[1];
+      totals[2] = mn[1];
+    }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double segment = __ddiv_rn(s_total, (double)n);
+  double p = __dadd_rn(__dmul_rn(uniforms[i], segment), __dmul_rn((double)i, segment));
+  int node = 1;
+  while (node < cap) {                   // segment_tree.py:124-130
+    const double left = sum[2 * node];
+    if (left > p) {
+      node = 2 * node;
+    } else {
+      p = __dsub_rn(p, left);
+      node = 2 * node + 1;
+    }
+  }
+  idx_out[i] = (int64_t)(node - cap);
+  leaf_out[i] = sum[node];
+}
+
+// SumSegmentTree.find_prefixsum_idx for a batch of given prefix sums (segment_tree.py:105-131).
+__global__ void __launch_bounds__(256) k_segtree_find(const double* __restrict__ sum, int cap, const double* __restrict__ prefix,
+                                                      int n, int64_t* __restrict__ idx_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p = prefix[i];
+  int node = 1;
+  while (node < cap) {
+    const double left = sum[2 * node];
+    if (left > p) {
+      node = 2 * node;
+    } else {
+      p = __dsub_rn(p, left);
+      node = 2 * node + 1;
+    }
+  }
+  idx_out[i] = (int64_t)(node - cap);
+}
+
+// replay_buffer.py:47-61 / :178-188 -- one warp per sampled row.
+__global__ void __launch_bounds__(256) k_buffer_gather(const double* __restrict__ storage, int ns, const int64_t* __restrict__ idx,
+                                                       int n, float* __restrict__ state, float* __restrict__ prtg,
+                                                       float* __restrict__ state_next, float* __restrict__ dVdx,
+                                                       float* __restrict__ done, double* __restrict__ term) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const int W = 3 * ns + 3;
+  const double* row = storage + (int64_t)idx[warp] * W;
+  for (int c = lane; c < W; c += 32) {
+    const double v = row[c];
+    if (c < ns) state[(int64_t)warp * ns + c] = (float)v;
+    else if (c == ns) prtg[warp] = (float)v;
+    else if (c < 2 * ns + 1) state_next[(int64_t)warp * ns + (c - ns - 1)] = (float)v;
+    else if (c < 3 * ns + 1) dVdx[(int64_t)warp * ns + (c - 2 * ns - 1)] = (float)v;
+    else if (c == 3 * ns + 1) done[warp] = (float)v;
+    else term[warp] = v;
+  }
+}
+
+// exp_counter[idx] += 1, a duplicated index counted once (NumPy fancy-index +=, replay_buffer.py:174).
+__global__ void __launch_bounds__(ST_THREADS) k_exp_counter(double* __restrict__ exp_counter, const int64_t* __restrict__ idx, int n,
+                                                            int* __restrict__ stamp) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += ST_THREADS) atomicMax(&stamp[(int)idx[i]], i);
+  __syncthreads();
+  for (int i = tid; i < n; i += ST_THREADS) {
+    const int j = (int)idx[i];
+    if (stamp[j] == i) {
+      exp_counter[j] = __dadd_rn(exp_counter[j], 1.0);
+      stamp[j] = -1;
+    }
+  }
+}
+
+}  // namespace cacto
+
+using namespace cacto;
+
+static bool pow2(int c) { return c > 0 && (c & (c - 1)) == 0; }
+
+extern "C" int cacto_segtree_update(double* sum_tree, double* min_tree, int32_t capacity, const int64_t* idx, const double* value,
+                                    int32_t n, int32_t* stamp, void* stream) {
+  if ((!sum_tree && !min_tree) || !idx || !value || !stamp) return CACTO_E_ARG;
+  if (!pow2(capacity) || capacity < 2 || n < 0) return CACTO_E_SIZE;
+  if (n == 0) return 0;
+  k_segtree_update<<<1, ST_THREADS, 0, (cudaStream_t)stream>>>(sum_tree, min_tree, capacity, idx, value, n, stamp);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_segtree_reduce(const double* sum_tree, const double* min_tree, int32_t capacity, int32_t start, int32_t end,
+                                    double* out, void* stream) {
+  if ((!sum_tree && !min_tree) || !out) return CACTO_E_ARG;
+  if (!pow2(capacity)) return CACTO_E_SIZE;
+  if (end < 0) end += capacity;          // segment_tree.py:71-72
+  end -= 1;                              // :73
+  if (start < 0 || end < start || end >= capacity) return CACTO_E_SIZE;
+  k_segtree_reduce<<<1, 32, 0, (cudaStream_t)stream>>>(sum_tree, min_tree, capacity, start, end, out);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_segtree_sample(const double* sum_tree, const double* min_tree, int32_t capacity, int32_t max_idx,
+                                    const double* uniforms, int32_t n, int64_t* idx, double* leaf, double* totals, void* stream) {
+  if (!sum_tree || !min_tree || !uniforms || !idx || !leaf || !totals) return CACTO_E_ARG;
+  if (!pow2(capacity) || n <= 0 || max_idx < 2 || max_idx > capacity) return CACTO_E_SIZE;
+  k_segtree_sample<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sum_tree, min_tree, capacity, max_idx, uniforms, n, idx, leaf,
+                                                                      totals);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_segtree_find(const double* sum_tree, int32_t capacity, const double* prefix, int32_t n, int64_t* idx,
+                                  void* stream) {
+  if (!sum_tree || !prefix || !idx) return CACTO_E_ARG;
+  if (!pow2(capacity) || n < 0) return CACTO_E_SIZE;
+  if (n == 0) return 0;
+  k_segtree_find<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sum_tree, capacity, prefix, n, idx);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_buffer_gather(const double* storage, int32_t ns, const int64_t* idx, int32_t n, float* state,
+                                   float* partial_rtg, float* state_next, float* dVdx, float* done, double* term,
+                                   double* exp_counter, int32_t* stamp, void* stream) {
+  if (!storage || !idx || !state || !partial_rtg || !state_next || !dVdx || !done || !term) return CACTO_E_ARG;
+  if (ns < 2 || ns > CACTO_MAX_NS || n < 0) return CACTO_E_SIZE;
+  if (exp_counter && !stamp) return CACTO_E_ARG;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_buffer_gather<<<(n * 32 + 255) / 256, 256, 0, st>>>(storage, ns, idx, n, state, partial_rtg, state_next, dVdx, done, term);
+  CACTO_LAUNCH_CHECK();
+  if (exp_counter) {
+    k_exp_counter<<<1, ST_THREADS, 0, st>>>(exp_counter, idx, n, stamp);
+    CACTO_LAUNCH_CHECK();
+  }
+  return 0;
+}

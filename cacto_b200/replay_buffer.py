@@ -1,0 +1,171 @@
+"""GPU replay buffers with the reference's ``replay_buffer.py`` interface.
+
+Storage (``storage_mat[REPLAY_SIZE, 3*ns+3]`` fp64, rows = [s, partial_rtg, s_next, dVdx, done, term],
+replay_buffer.py:20,72) lives in HBM; ``sample`` gathers the drawn rows with one kernel
+(``cacto_buffer_gather``) and returns float32 CUDA tensors, the analogue of
+``convert_sample_to_tensor`` (replay_buffer.py:74-83).
+
+Bit-exactness of indices and sampled transitions (BASELINE.md parity gate) is kept by leaving on the
+host exactly the parts whose bits depend on the host's libraries:
+  * the RNG streams -- ``np.random.randint`` for the uniform buffer (replay_buffer.py:45) and
+    ``random.random()`` for the PER strata (:153) -- are drawn on the host and shipped to the kernel;
+  * ``priority ** alpha`` and the importance weights ``(p * N) ** -beta`` use the host libm ``pow``
+    (CUDA's is not correctly rounded); they touch only B scalars per call.
+The tree walks (2B O(log N) Python loops + B descents per update in the reference) run in
+``cacto_segtree_update`` / ``cacto_segtree_sample``.
+
+The three reference bugs that make PER unusable as shipped (unqualified tree class
+names, ndarray passed to ``__getitem__``, ``RB_type`` never set) are fixed the obvious way; quirk Q4
+(the newest slot is excluded from the sampled mass) is reproduced because it changes indices.
+"""
+import random
+
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .segment_tree import MinSegmentTree, SumSegmentTree, _dev
+
+
+class ReplayBuffer(object):
+    """replay_buffer.py:9-83."""
+
+    def __init__(self, conf):
+        self.conf = conf
+        self.ns = int(conf.nb_state)
+        self.width = 3 * self.ns + 3
+        self.storage_mat = torch.zeros((conf.REPLAY_SIZE, self.width), dtype=torch.float64, device=_dev())
+        self.next_idx = 0
+        self.full = 0
+        self.exp_counter = np.zeros(conf.REPLAY_SIZE)
+
+    # replay_buffer.py:63-72
+    def concatenate_sample(self, obses_t, rewards, obses_t1, dVdxs, dones, terms):
+        cat = [np.concatenate([np.asarray(a, dtype=np.float64) for a in x], axis=0) for x in (obses_t, rewards, obses_t1, dVdxs, dones, terms)]
+        return np.concatenate((cat[0], cat[1].reshape(-1, 1), cat[2], cat[3], cat[4].reshape(-1, 1), cat[5].reshape(-1, 1)), axis=1)
+
+    def add(self, obses_t, rewards, obses_t1, dVdxs, dones, terms):
+        """replay_buffer.py:25-36 (ring write with wrap-around)."""
+        data = self.concatenate_sample(obses_t, rewards, obses_t1, dVdxs, dones, terms)
+        self.add_rows(torch.as_tensor(data).to(self.storage_mat.device))
+
+    def add_rows(self, data):
+        """Same as ``add`` for rows already concatenated ([n, 3ns+3] fp64, host or device)."""
+        data = data.to(self.storage_mat.device, torch.float64)
+        R, n = self.conf.REPLAY_SIZE, data.shape[0]
+        if n + self.next_idx > R:
+            self.storage_mat[self.next_idx:, :] = data[:R - self.next_idx, :]
+            self.storage_mat[:self.next_idx + n - R, :] = data[R - self.next_idx:, :]
+            self.full = 1
+        else:
+            self.storage_mat[self.next_idx:self.next_idx + n, :] = data
+        self._on_add(n)
+        self.next_idx = (self.next_idx + n) % R
+
+    def _on_add(self, n):
+        pass
+
+    def _max_idx(self):
+        return self.conf.REPLAY_SIZE if self.full else self.next_idx
+
+    def _gather(self, idx_dev):
+        n, ns, dev = idx_dev.numel(), self.ns, self.storage_mat.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        s, r, s1, dv, d = (torch.empty((n, ns), **f32), torch.empty((n, 1), **f32), torch.empty((n, ns), **f32),
+                           torch.empty((n, ns), **f32), torch.empty((n, 1), **f32))
+        term = torch.empty((n, 1), dtype=torch.float64, device=dev)
+        check(lib.cacto_buffer_gather(ptr(self.storage_mat), ns, ptr(idx_dev), n, ptr(s), ptr(r), ptr(s1), ptr(dv), ptr(d),
+                                      ptr(term), ptr(None), ptr(None), stream_ptr()), 'buffer_gather')
+        return s, r, s1, dv, d, term
+
+    def sample(self, idxes=None):
+        """replay_buffer.py:38-61.  ``idxes`` may be injected (the reference draws them from the global,
+        unseeded ``np.random``: quirk Q5)."""
+        if idxes is None:
+            idxes = np.random.randint(0, self._max_idx(), size=self.conf.BATCH_SIZE)
+        idx_dev = torch.as_tensor(np.asarray(idxes, dtype=np.int64)).to(self.storage_mat.device)
+        s, r, s1, dv, d, term = self._gather(idx_dev)
+        weights = torch.ones((idx_dev.numel(), 1), dtype=torch.float32, device=s.device)
+        return s, r, s1, dv, d, term, weights, None
+
+
+class PrioritizedReplayBuffer(ReplayBuffer):
+    """replay_buffer.py:87-240."""
+
+    def __init__(self, conf):
+        super().__init__(conf)
+        self.priorities = np.empty(conf.REPLAY_SIZE)
+        assert conf.prioritized_replay_alpha >= 0
+        assert conf.prioritized_replay_beta > 0
+        it_capacity = 1
+        while it_capacity < conf.REPLAY_SIZE:
+            it_capacity *= 2
+        self._capacity = it_capacity
+        self._it_sum = SumSegmentTree(it_capacity)
+        self._it_min = MinSegmentTree(it_capacity)
+        self._max_priority = 1.0
+        self.RB_type = 'PER'
+        dev = self.storage_mat.device
+        self._stamp = torch.full((it_capacity,), -1, dtype=torch.int32, device=dev)
+        self._totals = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def _tree_update(self, idx, val):
+        dev = self.storage_mat.device
+        idx = torch.as_tensor(np.asarray(idx, dtype=np.int64)).to(dev)
+        val = torch.as_tensor(np.asarray(val, dtype=np.float64)).to(dev)
+        check(lib.cacto_segtree_update(ptr(self._it_sum._value), ptr(self._it_min._value), self._capacity, ptr(idx), ptr(val),
+                                       idx.numel(), ptr(self._stamp), stream_ptr()), 'segtree_update')
+
+    def _on_add(self, n):
+        """replay_buffer.py:133-135: new rows enter with max_priority ** alpha in both trees."""
+        R = self.conf.REPLAY_SIZE
+        idx = (self.next_idx + np.arange(n)) % R
+        v = self._max_priority ** self.conf.prioritized_replay_alpha
+        self._tree_update(idx, np.full(n, v, dtype=np.float64))
+
+    def _sample_proportional(self, uniforms=None):
+        """replay_buffer.py:139-157.  Returns device idx, device leaf values, host totals
+        (sum(0, max_idx-1), sum(), min())."""
+        B = self.conf.BATCH_SIZE
+        if uniforms is None:
+            uniforms = np.array([random.random() for _ in range(B)])
+        dev = self.storage_mat.device
+        u = torch.as_tensor(np.asarray(uniforms, dtype=np.float64)).to(dev)
+        idx = torch.empty(B, dtype=torch.int64, device=dev)
+        leaf = torch.empty(B, dtype=torch.float64, device=dev)
+        check(lib.cacto_segtree_sample(ptr(self._it_sum._value), ptr(self._it_min._value), self._capacity, self._max_idx(), ptr(u), B,
+                                       ptr(idx), ptr(leaf), ptr(self._totals), stream_ptr()), 'segtree_sample')
+        return idx, leaf
+
+    def sample(self, uniforms=None):
+        """replay_buffer.py:159-188."""
+        max_idx = self._max_idx()
+        beta = self.conf.prioritized_replay_beta
+        idx_dev, leaf_dev = self._sample_proportional(uniforms)
+        s, r, s1, dv, d, term = self._gather(idx_dev)
+        # one small D2H: B indices + B leaves + 3 totals; the pow() below must be the host's (bit-exactness)
+        batch_idxes = idx_dev.cpu().numpy().astype(int)
+        leaf = leaf_dev.cpu().numpy()
+        _, tot, mn = self._totals.cpu().numpy()
+        p_min = mn / tot
+        max_weight = (p_min * max_idx) ** (-beta)
+        self.exp_counter[batch_idxes] += 1
+        self.priorities[batch_idxes] = leaf / tot
+        weights = (self.priorities[batch_idxes] * max_idx) ** (-beta) / max_weight
+        weights = torch.as_tensor(weights.astype(np.float32)).to(s.device)
+        return s, r, s1, dv, d, term, weights, batch_idxes
+
+    def update_priorities(self, idxes, reward_to_go_batch, critic_value, target_critic_value=None):
+        """replay_buffer.py:190-218 ('PER' branch)."""
+        c = self.conf
+        rtg = torch.as_tensor(reward_to_go_batch).reshape(-1, 1)
+        V = torch.as_tensor(critic_value).reshape(-1, 1)
+        td = torch.abs(rtg.to(torch.float32) - V.to(torch.float32))[:, 0].cpu().numpy()
+        idxes = np.asarray(idxes).astype(int)
+        fresh = c.fresh_factor ** self.exp_counter[idxes]
+        new_p = fresh * td + c.prioritized_replay_eps
+        assert len(idxes) == len(new_p)
+        assert (new_p > 0).all()
+        vals = np.array([p ** c.prioritized_replay_alpha for p in new_p], dtype=np.float64)
+        self._tree_update(idxes, vals)
+        self._max_priority = max(self._max_priority, float(new_p.max()))

@@ -1,0 +1,38 @@
+"""Batched n-step reward-to-go (kernel K5) -- the arithmetic of RL_AC.RL_Solve (RL.py:173-187).
+
+``rtg_batch`` processes a ragged batch of TO trajectories in one launch of ``cacto_rtg_window``;
+``RL.RL_AC.RL_Solve`` calls it with a single trajectory to keep the reference's method signature.
+"""
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .segment_tree import _dev
+
+
+def rtg_batch(conf, states_list, step_cost_list):
+    """states_list[e]: [T_e+1, ns] (TO_states with the time column, TO.py:114-115);
+    step_cost_list[e]: [T_e+1] TO step costs (reward = -cost, RL.py:168).
+    Returns a dict of CUDA fp64 tensors over the concatenated knots plus ``offsets`` (host int64):
+    partial, total, state_next, done, term, rwrd, ep_return[E]."""
+    ns = int(conf.nb_state)
+    lens = np.array([len(c) for c in step_cost_list], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    dev = _dev()
+    if isinstance(states_list, torch.Tensor):
+        states = states_list.to(dev, torch.float64).contiguous()
+        rwrd = (-step_cost_list.to(dev, torch.float64)).contiguous() if isinstance(step_cost_list, torch.Tensor) else None
+    else:
+        states = torch.as_tensor(np.concatenate([np.asarray(s, dtype=np.float64).reshape(-1, ns) for s in states_list], axis=0)).to(dev)
+        rwrd = torch.as_tensor(-np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1) for c in step_cost_list])).to(dev)
+    total_knots = int(offsets[-1])
+    E = len(lens)
+    off_dev = torch.as_tensor(offsets).to(dev)
+    f64 = dict(dtype=torch.float64, device=dev)
+    out = dict(partial=torch.empty(total_knots, **f64), total=torch.empty(total_knots, **f64),
+               state_next=torch.empty((total_knots, ns), **f64), done=torch.empty(total_knots, **f64),
+               term=torch.empty(total_knots, **f64), ep_return=torch.empty(E, **f64), rwrd=rwrd, states=states, offsets=offsets)
+    check(lib.cacto_rtg_window(ptr(off_dev), E, ptr(rwrd), ptr(states), ns, int(getattr(conf, 'nsteps_TD_N', 0)), int(bool(conf.MC)),
+                               ptr(out['partial']), ptr(out['total']), ptr(out['state_next']), ptr(out['done']), ptr(out['term']),
+                               ptr(out['ep_return']), stream_ptr()), 'rtg_window')
+    return out

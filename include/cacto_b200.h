@@ -1,0 +1,190 @@
+/* cacto_b200.h -- C ABI of libcacto_b200.so: the B200 (sm_100a) implementation of CACTO's
+ * data-parallel learning hot path.
+ *
+ * The reference (nadimkanazi/cacto) is pure Python with no FFI of its own; its drop-in boundary is
+ * the module API wired in main.py:145-151.  Every entry point below names the reference method(s)
+ * whose arithmetic it replaces; the Python host in cacto_b200/ keeps those methods' names and
+ * signatures and calls these symbols through ctypes.
+ *
+ * Conventions (all entry points):
+ *   - device pointers only, caller owns every buffer, nothing is allocated or freed here;
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*), no hidden synchronisation;
+ *   - returns 0 on success, a negative CACTO_E_* on bad arguments, a positive cudaError_t on
+ *     launch failure; never throws, never prints;
+ *   - no global mutable state: system constants travel in the POD cacto_sys_params.
+ *   - dtype: 0 = float32, 1 = float64.  layout: 0 = rows [B][width] (the reference's batch API),
+ *     1 = structure-of-arrays [width][B] (coalesced; used by the rollout trajectories).
+ */
+#ifndef CACTO_B200_H
+#define CACTO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CACTO_ABI_VERSION 1
+
+enum { CACTO_E_ARG = -1, CACTO_E_SYSTEM = -2, CACTO_E_DTYPE = -3, CACTO_E_SIZE = -4, CACTO_E_ALIGN = -5 };
+
+enum cacto_system {
+  CACTO_SINGLE_INTEGRATOR = 0, /* environment.py:165 */
+  CACTO_DOUBLE_INTEGRATOR = 1, /* environment.py:288 + urdf/double_integrator.urdf */
+  CACTO_CAR = 2,               /* environment.py:364 */
+  CACTO_CAR_PARK = 3,          /* environment.py:493 */
+  CACTO_MANIPULATOR = 4,       /* environment.py:654 + urdf/planar_manipulator_3dof.urdf */
+  CACTO_UR5 = 5                /* environment.py:736 + urdf/ur5_robot.urdf */
+};
+
+#define CACTO_MAX_NS 13
+#define CACTO_MAX_NA 6
+#define CACTO_MAX_JOINTS 6
+
+/* Serial chain extracted from the URDF (what Pinocchio builds in conf_*.py: RobotWrapper.BuildFromURDF). */
+typedef struct {
+  int32_t n;                            /* joints */
+  int32_t jtype[CACTO_MAX_JOINTS];      /* 0 revolute, 1 prismatic */
+  int32_t axis[CACTO_MAX_JOINTS];       /* 0 x, 1 y, 2 z */
+  double p[CACTO_MAX_JOINTS][3];        /* joint origin in the parent frame */
+  double R[CACTO_MAX_JOINTS][9];        /* fixed rotation parent->joint frame, row-major (rpy) */
+  double mass[CACTO_MAX_JOINTS];
+  double com[CACTO_MAX_JOINTS][3];
+  double inertia[CACTO_MAX_JOINTS][6];  /* ixx iyy izz ixy ixz iyz about the COM */
+  double ee_p[3];                       /* EE frame on the last link */
+  double gravity;                       /* 9.81 */
+} cacto_chain;
+
+/* Everything the kernels read from conf_<system>.py. */
+typedef struct {
+  int32_t system;      /* enum cacto_system */
+  int32_t nx, ns, na;  /* ns = nx + 1 (time is the last state) */
+  int32_t normalize;   /* conf.NORMALIZE_INPUTS */
+  int32_t pad_;
+  double dt;
+  double state_norm[CACTO_MAX_NS + 3];  /* conf.state_norm_arr (ns entries) */
+  double u_max[CACTO_MAX_NA + 2];
+  /* cost function (environment.py reward(), Appendix A.1 of SURVEY.md) */
+  double scale, offset, alpha, alpha2, w_b;
+  double target[3];
+  double obs[18];            /* conf.obs_param */
+  double L_delta, tau_delta, k_db;
+  double check_points[20];   /* car_park body check points (10 x 2) */
+  double w_running[8], w_terminal[8];
+  cacto_chain chain;
+} cacto_sys_params;
+
+/* MLP parameter blocks: one contiguous float32 buffer per network, Keras order
+ * [W1 (in x out, row-major), b1, W2, b2, ...].  Actor: ns->256->256->na (NeuralNetwork.py:51-63).
+ * Critic 'sine': ns->64->64->128->128->1 (NeuralNetwork.py:95-108). */
+int64_t cacto_actor_param_count(int32_t ns, int32_t na);
+int64_t cacto_critic_param_count(int32_t ns);
+int32_t cacto_abi_version(void);
+
+/* ---- K1': Env.simulate_batch (environment.py:134-138; per system :235,:437,:584, robot_utils.py:399-405) */
+int cacto_dyn_step(const cacto_sys_params* p, int dtype, int layout, const void* state, const void* action,
+                   void* state_next, int64_t B, void* stream);
+
+/* ---- K2: Env.derivative_batch (environment.py:140-144,93-109): Fu[B][ns][na], normalised, time row 0 */
+int cacto_dyn_derivative(const cacto_sys_params* p, int dtype, int layout, const void* state, const void* action,
+                         void* Fu, int64_t B, void* stream);
+
+/* ---- K2: Env.augmented_derivative over a batch (environment.py:111-132,:221,:420,:567; caller TO.py:181):
+ *      Fx[B][nx][nx], Fu[B][nx][na] */
+int cacto_dyn_augmented(const cacto_sys_params* p, int dtype, int layout, const void* state, const void* action,
+                        void* Fx, void* Fu, int64_t B, void* stream);
+
+/* ---- Env.get_end_effector_position over a batch (environment.py:146-156,:245,:450,:597): ee[B][3] */
+int cacto_ee_position(const cacto_sys_params* p, int dtype, int layout, const void* state, void* ee, int64_t B,
+                      void* stream);
+
+/* ---- Env.reward / reward_batch (environment.py:252-286 and twins; UR5 :780-816).
+ *      weights[B][8] (fp64, conf.cost_weights_*), action may be NULL (reward(w, s)).
+ *      ur5_plain_ucost != 0 selects UR5.reward's u.u control cost (quirk Q8) instead of the bounded one.
+ *      reward[B]; dr_da[B][na] optional (NULL to skip) = d reward / d action (NeuralNetwork.py:199-204). */
+int cacto_reward(const cacto_sys_params* p, int dtype, int layout, const double* weights, const void* state,
+                 const void* action, int ur5_plain_ucost, void* reward, void* dr_da, int64_t B, void* stream);
+
+/* ---- K1: RL_AC.create_TO_init over a batch (RL.py:197-233) fused with the actor forward
+ *      (NeuralNetwork.py:130-138, utils.py:17-24) and Env.simulate.
+ *      ics[B][ns] fp64; horizon[B] int32 (NSTEPS_SH per rollout, <= T_max); use_actor = (ep != 0).
+ *      states  [T_max+1][ns][B] fp64 (SoA, time-major), controls [T_max][na][B] fp64,
+ *      flags[B] int32: 1 ok, 0 NaN met (RL.py:229-231).  Entries past a rollout's horizon are left untouched.
+ *      If reward_weights != NULL also writes rewards[T_max+1][B] = Env.step's reward at the current
+ *      state/action with the running weights, terminal weights at the last knot (plot_utils.py:261-268). */
+int cacto_rollout(const cacto_sys_params* p, const float* actor_params, int use_actor, const double* ics,
+                  const int32_t* horizon, int32_t T_max, double* states, double* controls, int32_t* flags,
+                  double* rewards, int64_t B, void* stream);
+
+/* ---- N4: NN.eval over a batch (NeuralNetwork.py:130-138): out[B][na] (actor) / out[B][1] (critic) */
+int cacto_actor_forward(const cacto_sys_params* p, const float* actor_params, const float* state, float* out,
+                        int64_t B, void* stream);
+int cacto_critic_forward(const cacto_sys_params* p, const float* critic_params, const float* state, float* value,
+                         float* dV_ds /* [B][ns] or NULL */, int64_t B, void* stream);
+
+/* ---- N6: NN.compute_critic_grad (NeuralNetwork.py:150-178).
+ *      grad (float32, critic_param_count) is ACCUMULATED into (caller zeroes it); inv_B = 1/global batch.
+ *      Outputs rtg[B], V[B], V_target_s[B] (the reference's return tuple). */
+int cacto_critic_grad(const cacto_sys_params* p, const float* critic_params, const float* critic_params_T,
+                      const float* target_params, float w_S, int mc, const float* state, const float* state_next,
+                      const float* partial_rtg, const float* dVdx, const float* done, const float* weights,
+                      float inv_B, float* grad, float* rtg, float* V, float* V_target_s, float* loss,
+                      int64_t B, void* stream);
+
+/* ---- N7: NN.compute_actor_grad (NeuralNetwork.py:180-232) incl. simulate_batch / derivative_batch /
+ *      reward_batch inside the kernel.  term[B] fp64 as the reference keeps it. */
+int cacto_actor_grad(const cacto_sys_params* p, const float* actor_params, const float* actor_params_T,
+                     const float* critic_params, const float* critic_params_T, const float* state,
+                     const double* term, float inv_B, float* grad, float* actions /* [B][na] or NULL */,
+                     int64_t B, void* stream);
+
+/* ---- N8/N9: tf.keras Adam step (RL.py:105,109) with optional transposed-copy refresh and Polyak
+ *      target update (RL.py:113-118).  alpha_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller. */
+int cacto_adam_step(float* params, const float* grad, float* m, float* v, float alpha_t, float beta1, float beta2,
+                    float eps, float* target_or_null, float tau, int64_t n, void* stream);
+
+/* Rebuild the per-layer transposed copy of a parameter block (W^T per layer, biases copied). */
+int cacto_transpose_params(const float* params, float* params_T, int32_t is_critic, int32_t ns, int32_t na,
+                           void* stream);
+
+/* ---- R3/K4: segment_tree.py.  Trees are fp64 arrays of 2*capacity nodes, root at 1.
+ *      update: tree[idx[i]] = value[i] in batch order (last duplicate wins), then every touched ancestor is
+ *      recomputed level by level (SegmentTree.__setitem__, segment_tree.py:76-86).  Either tree may be NULL. */
+int cacto_segtree_update(double* sum_tree, double* min_tree, int32_t capacity, const int64_t* idx,
+                         const double* value, int32_t n, int32_t* stamp /* [capacity] workspace, all -1 */,
+                         void* stream);
+/* SumSegmentTree.sum(start, end) / MinSegmentTree.min(start, end): out[0] = sum, out[1] = min,
+ * Python slice semantics of segment_tree.py:51-74 (end exclusive, negative end wraps). */
+int cacto_segtree_reduce(const double* sum_tree, const double* min_tree, int32_t capacity, int32_t start,
+                         int32_t end, double* out, void* stream);
+/* PrioritizedReplayBuffer._sample_proportional (replay_buffer.py:139-157) + the leaf read of :175:
+ * uniforms[n] are the host's random.random() draws; idx[n] int64, leaf[n] fp64 = sum_tree[idx],
+ * totals[0] = sum(0, max_idx-1) used for the strata, totals[1] = sum(), totals[2] = min(). */
+int cacto_segtree_sample(const double* sum_tree, const double* min_tree, int32_t capacity, int32_t max_idx,
+                         const double* uniforms, int32_t n, int64_t* idx, double* leaf, double* totals,
+                         void* stream);
+
+/* SumSegmentTree.find_prefixsum_idx (segment_tree.py:105-131) for n given prefix sums. */
+int cacto_segtree_find(const double* sum_tree, int32_t capacity, const double* prefix, int32_t n, int64_t* idx,
+                       void* stream);
+
+/* ---- R1/R2: gather of sampled rows (replay_buffer.py:47-61,178-188): storage[cap][3ns+3] fp64 ->
+ *      float32 blocks; term stays fp64.  exp_counter (fp64[cap]) is incremented once per distinct index
+ *      when non-NULL (replay_buffer.py:174). */
+int cacto_buffer_gather(const double* storage, int32_t ns, const int64_t* idx, int32_t n, float* state,
+                        float* partial_rtg, float* state_next, float* dVdx, float* done, double* term,
+                        double* exp_counter, int32_t* stamp, void* stream);
+
+/* ---- G1/K5: RL_AC.RL_Solve windows (RL.py:173-187) for a ragged batch of trajectories.
+ *      offsets[E+1] (knot offsets, trajectory e has T_e+1 = offsets[e+1]-offsets[e] knots),
+ *      rwrd[total] fp64, states[total][ns] fp64 ->
+ *      partial[total], total_rtg[total] (float32-rounded, stored fp64), s_next[total][ns], done[total],
+ *      term[total], ep_return[E]. */
+int cacto_rtg_window(const int64_t* offsets, int32_t E, const double* rwrd, const double* states, int32_t ns,
+                     int32_t nsteps_td, int32_t mc, double* partial, double* total_rtg, double* s_next,
+                     double* done, double* term, double* ep_return, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CACTO_B200_H */

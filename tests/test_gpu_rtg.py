@@ -1,0 +1,48 @@
+"""CUDA reward-to-go windows: bit-exact against RL_AC.RL_Solve goldens and the oracle."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import rtg as ortg
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rtg_matches_reference_goldens():
+    from cacto_b200.rtg import rtg_batch
+    g = golden('rtg_cases.npz')
+    for k in range(int(g['ncases'])):
+        T, n, MC, ns = [int(x) for x in g[f'c{k}_meta']]
+        conf = SimpleNamespace(nb_state=ns, MC=MC, nsteps_TD_N=n)
+        out = rtg_batch(conf, [g[f'c{k}_states']], [g[f'c{k}_cost']])
+        np.testing.assert_array_equal(out['partial'].cpu().numpy(), g[f'c{k}_partial'])
+        np.testing.assert_array_equal(out['total'].cpu().numpy(), g[f'c{k}_total'])
+        np.testing.assert_array_equal(out['state_next'].cpu().numpy(), g[f'c{k}_snext'])
+        np.testing.assert_array_equal(out['done'].cpu().numpy(), g[f'c{k}_done'])
+        np.testing.assert_array_equal(out['term'].cpu().numpy(), g[f'c{k}_term'])
+        np.testing.assert_array_equal(out['rwrd'].cpu().numpy(), g[f'c{k}_rwrd'])
+        assert float(out['ep_return'][0]) == float(g[f'c{k}_ret'])
+
+
+def test_ragged_batch_matches_oracle():
+    """EP_UPDATE = 200 trajectories of ragged length (manipulator sizes: T <= 100, n = 50)."""
+    from cacto_b200.rtg import rtg_batch
+    rng = np.random.default_rng(0)
+    conf = SimpleNamespace(nb_state=7, MC=0, nsteps_TD_N=50)
+    lens = rng.integers(1, 101, 200)
+    lens[0], lens[1] = 100, 1
+    states = [rng.normal(size=(T + 1, 7)) for T in lens]
+    costs = [rng.uniform(0, 2, T + 1) * 10.0 ** rng.integers(-5, 1, T + 1) for T in lens]
+    out = rtg_batch(conf, states, costs)
+    off = out['offsets']
+    for e in range(200):
+        _, partial, total, snext, done, rwrd, term, ret = ortg.rl_solve(conf, states[e], costs[e])
+        sl = slice(off[e], off[e + 1])
+        np.testing.assert_array_equal(out['partial'][sl].cpu().numpy(), partial)
+        np.testing.assert_array_equal(out['total'][sl].cpu().numpy(), total)
+        np.testing.assert_array_equal(out['state_next'][sl].cpu().numpy(), snext)
+        np.testing.assert_array_equal(out['done'][sl].cpu().numpy(), done)
+        np.testing.assert_array_equal(out['term'][sl].cpu().numpy(), term)
+        assert float(out['ep_return'][e]) == ret
