@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's ``RL.py`` (class ``RL_AC``) on the CUDA hot path.
+
+  setup_model        RL.py:61-99    networks + Adam (+ PiecewiseConstantDecay when conf.LR_SCHEDULE)
+  update             RL.py:101-111  critic gradient -> Adam, then actor gradient (with the UPDATED critic) -> Adam
+  update_target      RL.py:113-118  Polyak averaging
+  learn_and_update   RL.py:120-143  sample -> update -> priorities -> target
+  RL_Solve           RL.py:145-189  n-step reward-to-go of one TO trajectory (kernel K5)
+  create_TO_init     RL.py:197-233  policy rollout warm-start of one initial condition (kernel K1)
+plus the batched entry points the reference lacks and the metric needs:
+  rollout_batch(ICS[B, ns], ep)     all warm-starts of an episode batch in one launch
+  rtg_batch(...)                    all reward-to-go windows of an episode batch in one launch
+Data parallelism (``dist`` = an initialised torch.distributed group): each rank passes its shard of the
+minibatch, gradients are summed with one NCCL all-reduce per network before the Adam step
+(critic and actor steps are sequentially dependent, RL.py:104-109).
+"""
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .environment import _as_cuda, _device
+from .optim import Adam, PiecewiseConstantDecay
+from .rtg import rtg_batch as _rtg_batch
+
+
+class RL_AC:
+    def __init__(self, env, NN, conf, N_try, dist=None):
+        self.env = env
+        self.NN = NN
+        self.conf = conf
+        self.N_try = N_try
+        self.dist = dist
+
+        self.actor_model = None
+        self.critic_model = None
+        self.target_critic = None
+        self.actor_optimizer = None
+        self.critic_optimizer = None
+
+        self.init_rand_state = None
+        self.NSTEPS_SH = 0
+        self.control_arr = None
+        self.state_arr = None
+        self.ee_pos_arr = None
+        self.exp_counter = np.zeros(conf.REPLAY_SIZE)
+
+    # ------------------------------------------------------------------------------ models
+    def setup_model(self, recover_training=None):
+        """RL.py:61-99."""
+        c = self.conf
+        self.actor_model = self.NN.create_actor()
+        if c.critic_type == 'sine':
+            self.critic_model = self.NN.create_critic_sine()
+            self.target_critic = self.NN.create_critic_sine()
+        elif c.critic_type == 'elu':
+            self.critic_model, self.target_critic = self.NN.create_critic_elu(), self.NN.create_critic_elu()
+        elif c.critic_type == 'sine-elu':
+            self.critic_model, self.target_critic = self.NN.create_critic_sine_elu(), self.NN.create_critic_sine_elu()
+        else:
+            self.critic_model, self.target_critic = self.NN.create_critic_relu(), self.NN.create_critic_relu()
+
+        if c.LR_SCHEDULE:
+            self.CRITIC_LR_SCHEDULE = PiecewiseConstantDecay(c.boundaries_schedule_LR_C, c.values_schedule_LR_C)
+            self.ACTOR_LR_SCHEDULE = PiecewiseConstantDecay(c.boundaries_schedule_LR_A, c.values_schedule_LR_A)
+            self.critic_optimizer = Adam(self.CRITIC_LR_SCHEDULE)
+            self.actor_optimizer = Adam(self.ACTOR_LR_SCHEDULE)
+        else:
+            self.critic_optimizer = Adam(c.CRITIC_LEARNING_RATE)
+            self.actor_optimizer = Adam(c.ACTOR_LEARNING_RATE)
+
+        if recover_training is not None:
+            path, n_try, step = str(recover_training[0]), recover_training[1], recover_training[2]
+            self.actor_model.load_weights("{}/N_try_{}/actor_{}".format(path, n_try, step))
+            self.critic_model.load_weights("{}/N_try_{}/critic_{}".format(path, n_try, step))
+            self.target_critic.load_weights("{}/N_try_{}/target_critic_{}".format(path, n_try, step))
+        else:
+            self.target_critic.set_weights(self.critic_model.get_weights())
+        if self.dist is not None:                       # identical replicas: broadcast rank 0's initial weights
+            for net in (self.actor_model, self.critic_model, self.target_critic):
+                self.dist.broadcast(net.params, src=0)
+                net.refresh_transposed()
+
+    # ------------------------------------------------------------------------------ update
+    def _allreduce(self, net):
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(net.grad)             # NCCL sum over NVLink; each rank used 1/global_batch
+
+    def update(self, state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
+               batch_size=None, fuse_target=False):
+        """RL.py:101-111.  ``fuse_target`` additionally performs update_target inside the critic's Adam launch
+        (used by learn_and_update; the target is only read again at the next critic gradient, so the result is
+        identical to calling update_target afterwards)."""
+        world = self.dist.get_world_size() if self.dist is not None else 1
+        gb = state_batch.shape[0] * world
+        critic_grad, reward_to_go_batch, critic_value, target_critic_value = self.NN.compute_critic_grad(
+            self.critic_model, self.target_critic, state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch,
+            weights_batch, global_batch=gb)
+        self._allreduce(self.critic_model)
+        if fuse_target and not self.conf.MC:
+            self.critic_optimizer.step(self.critic_model, target=self.target_critic, tau=self.conf.UPDATE_RATE)
+        else:
+            self.critic_optimizer.apply_gradients(zip(critic_grad, self.critic_model.trainable_variables))
+
+        actor_grad = self.NN.compute_actor_grad(self.actor_model, self.critic_model, state_batch, term_batch, batch_size, global_batch=gb)
+        self._allreduce(self.actor_model)
+        self.actor_optimizer.apply_gradients(zip(actor_grad, self.actor_model.trainable_variables))
+        return reward_to_go_batch, critic_value, target_critic_value
+
+    def update_target(self, target_weights, weights):
+        """RL.py:113-118: a <- b * tau + a * (1 - tau)."""
+        tau = float(self.conf.UPDATE_RATE)
+        for a, b in zip(target_weights, weights):
+            a.copy_(b * tau + a * (1 - tau))
+
+    def learn_and_update(self, update_step_counter, buffer, ep):
+        """RL.py:120-143."""
+        for _ in range(int(self.conf.UPDATE_LOOPS[ep])):
+            state_batch, partial_reward_to_go_batch, state_next_rollout_batch, dVdx_batch, d_batch, term_batch, weights_batch, batch_idxes = buffer.sample()
+            reward_to_go_batch, critic_value, target_critic_value = self.update(
+                state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
+                fuse_target=True)
+            if self.conf.prioritized_replay_alpha != 0:
+                buffer.update_priorities(batch_idxes, reward_to_go_batch, critic_value, target_critic_value)
+            update_step_counter += 1
+            if update_step_counter % self.conf.save_interval == 0:
+                self.RL_save_weights(update_step_counter)
+        return update_step_counter
+
+    def RL_save_weights(self, update_step_counter='final'):
+        """RL.py:191-195 (npz instead of Keras .h5)."""
+        import os
+        d = self.conf.NNs_path + "/N_try_{}".format(self.N_try)
+        os.makedirs(d, exist_ok=True)
+        self.actor_model.save_weights(d + "/actor_{}".format(update_step_counter))
+        self.critic_model.save_weights(d + "/critic_{}".format(update_step_counter))
+        self.target_critic.save_weights(d + "/target_critic_{}".format(update_step_counter))
+
+    # ------------------------------------------------------------------------------ reward-to-go
+    def rtg_batch(self, TO_states_list, TO_step_cost_list):
+        return _rtg_batch(self.conf, TO_states_list, TO_step_cost_list)
+
+    def RL_Solve(self, TO_controls, TO_states, TO_step_cost):
+        """RL.py:145-189 for env_RL = 0 (every conf): returns the reference's 9-tuple (NumPy)."""
+        if self.conf.env_RL:
+            raise NotImplementedError('env_RL = 1 (re-simulating the TO controls) is not on the hot path; every conf sets env_RL = 0')
+        self.control_arr = TO_controls
+        out = _rtg_batch(self.conf, [TO_states], [TO_step_cost])
+        self.state_arr = np.asarray(TO_states)
+        rwrd_arr = -np.asarray(TO_step_cost, dtype=np.float64)
+        cpu = lambda k: out[k].cpu().numpy()
+        return (self.state_arr, cpu('partial'), cpu('total'), cpu('state_next'), cpu('done'), rwrd_arr, cpu('term'),
+                float(out['ep_return'][0]), self.ee_pos_arr)
+
+    # ------------------------------------------------------------------------------ rollouts
+    def horizon(self, ICS):
+        """NSTEPS_SH = NSTEPS - int(t0 / dt) (RL.py:201): fp64 division, truncation -- evaluated on the host in fp64."""
+        ICS = np.asarray(ICS, dtype=np.float64).reshape(-1, self.conf.nb_state)
+        return (self.conf.NSTEPS - (ICS[:, -1] / self.conf.dt).astype(np.int64)).astype(np.int32)
+
+    def rollout_batch(self, ICS, ep, horizon=None, with_reward=False):
+        """All warm-starts of RL.py:197-233 for ICS[B, ns] in one launch of the fused actor+dynamics kernel.
+        Returns a dict: states [T_max+1, ns, B] and controls [T_max, na, B] (fp64, structure-of-arrays, time-major;
+        ``states.permute(2, 0, 1)`` is the reference's per-rollout [T+1, ns] view), horizon [B] (NSTEPS_SH),
+        success [B] (0 where a NaN was met, RL.py:229-231), optionally rewards [T_max+1, B]."""
+        c = self.conf
+        dev = _device()
+        ics = _as_cuda(ICS, torch.float64).reshape(-1, c.nb_state)
+        B = ics.shape[0]
+        if horizon is None:
+            horizon = self.horizon(ics.cpu().numpy() if isinstance(ICS, torch.Tensor) else ICS)
+        hz = torch.as_tensor(np.asarray(horizon, dtype=np.int32)).to(dev) if not isinstance(horizon, torch.Tensor) else horizon.to(dev, torch.int32)
+        T_max = int(c.NSTEPS)
+        states = torch.full((T_max + 1, c.nb_state, B), float('nan'), dtype=torch.float64, device=dev)
+        controls = torch.full((T_max, c.nb_action, B), float('nan'), dtype=torch.float64, device=dev)
+        flags = torch.empty(B, dtype=torch.int32, device=dev)
+        rewards = torch.full((T_max + 1, B), float('nan'), dtype=torch.float64, device=dev) if with_reward else None
+        use_actor = int(ep != 0)
+        actor = self.actor_model.params if use_actor else None
+        check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
+                                ptr(rewards), B, stream_ptr()), 'rollout')
+        out = dict(states=states, controls=controls, horizon=hz, success=flags)
+        if with_reward:
+            out['rewards'] = rewards
+        return out
+
+    def create_TO_init(self, ep, ICS):
+        """RL.py:197-233 for one initial condition -> (ICS, init_TO_states[T+1, ns], init_TO_controls[T, na], T, success)."""
+        self.init_rand_state = ICS
+        self.NSTEPS_SH = int(self.horizon(ICS)[0])
+        if self.NSTEPS_SH == 0:
+            return None, None, None, None, 0
+        T = self.NSTEPS_SH
+        r = self.rollout_batch(np.asarray(ICS, dtype=np.float64).reshape(1, -1), ep)
+        if int(r['success'][0]) == 0:
+            return None, None, None, None, 0
+        init_TO_states = r['states'][:T + 1, :, 0].cpu().numpy()
+        init_TO_controls = r['controls'][:T, :, 0].cpu().numpy()
+        self.control_arr = np.empty((T, self.conf.nb_action))
+        self.state_arr = np.empty((T + 1, self.conf.nb_state))
+        self.ee_pos_arr = np.empty((T + 1, 3))
+        self.state_arr[0, :] = ICS
+        self.ee_pos_arr[0, :] = self.env.get_end_effector_position(self.state_arr[0, :])
+        return self.init_rand_state, init_TO_states, init_TO_controls, self.NSTEPS_SH, 1

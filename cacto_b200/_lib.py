@@ -92,15 +92,16 @@ _SIGNATURES = {
     'cacto_ee_position': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_reward': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int64, C.c_void_p]),
-    #TODO 'cacto_rollout': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-    #TODO C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    #TODO 'cacto_actor_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    #TODO 'cacto_critic_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    #TODO 'cacto_critic_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 6 +
-    #TODO [C.c_float] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]),
-    #TODO 'cacto_actor_grad': (C.c_int, [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    #TODO 'cacto_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_float] * 4 + [C.c_void_p, C.c_float, C.c_int64, C.c_void_p]),
-    #TODO 'cacto_transpose_params': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    'cacto_rollout': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_actor_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_critic_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_critic_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 6 +
+    [C.c_float] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]),
+    'cacto_actor_grad': (C.c_int, [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_float] * 4 + [C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int64, C.c_void_p]),
+    'cacto_transpose_params': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'cacto_segtree_update': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'cacto_segtree_reduce': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'cacto_segtree_sample': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

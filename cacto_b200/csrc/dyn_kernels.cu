@@ -252,8 +252,8 @@ using namespace cacto;
 extern "C" int cacto_dyn_step(const cacto_sys_params* p, int dtype, int layout, const void* state, const void* action,
                               void* state_next, int64_t B, void* stream) {
   if (int e = check_common(p, dtype, layout, B)) return e;
-  if (!state || !action || !state_next) return CACTO_E_ARG;
   if (B == 0) return 0;
+  if (!state || !action || !state_next) return CACTO_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
 #define M_(SYS) DISPATCH_TL(SYS, launch_step, *p, state, action, state_next, B, st)
   CACTO_FOR_SYSTEM(p->system, M_)
@@ -265,8 +265,8 @@ extern "C" int cacto_dyn_derivative(const cacto_sys_params* p, int dtype, int la
                                     void* Fu, int64_t B, void* stream) {
   (void)action;  // ds'/da does not depend on a for any of the six systems (environment.py:93-109)
   if (int e = check_common(p, dtype, layout, B)) return e;
-  if (!state || !Fu) return CACTO_E_ARG;
   if (B == 0) return 0;
+  if (!state || !Fu) return CACTO_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
 #define M_(SYS) DISPATCH_TL(SYS, launch_derivative, *p, state, Fu, B, st)
   CACTO_FOR_SYSTEM(p->system, M_)
@@ -277,8 +277,8 @@ extern "C" int cacto_dyn_derivative(const cacto_sys_params* p, int dtype, int la
 extern "C" int cacto_dyn_augmented(const cacto_sys_params* p, int dtype, int layout, const void* state, const void* action,
                                    void* Fx, void* Fu, int64_t B, void* stream) {
   if (int e = check_common(p, dtype, layout, B)) return e;
-  if (!state || !action || !Fx || !Fu) return CACTO_E_ARG;
   if (B == 0) return 0;
+  if (!state || !action || !Fx || !Fu) return CACTO_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
 #define M_(SYS) DISPATCH_TL(SYS, launch_augmented, *p, state, action, Fx, Fu, B, st)
   CACTO_FOR_SYSTEM(p->system, M_)
@@ -289,8 +289,8 @@ extern "C" int cacto_dyn_augmented(const cacto_sys_params* p, int dtype, int lay
 extern "C" int cacto_ee_position(const cacto_sys_params* p, int dtype, int layout, const void* state, void* ee, int64_t B,
                                  void* stream) {
   if (int e = check_common(p, dtype, layout, B)) return e;
-  if (!state || !ee) return CACTO_E_ARG;
   if (B == 0) return 0;
+  if (!state || !ee) return CACTO_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
 #define M_(SYS) DISPATCH_TL(SYS, launch_ee, *p, state, ee, B, st)
   CACTO_FOR_SYSTEM(p->system, M_)
@@ -301,9 +301,9 @@ extern "C" int cacto_ee_position(const cacto_sys_params* p, int dtype, int layou
 extern "C" int cacto_reward(const cacto_sys_params* p, int dtype, int layout, const double* weights, const void* state,
                             const void* action, int ur5_plain_ucost, void* reward, void* dr_da, int64_t B, void* stream) {
   if (int e = check_common(p, dtype, layout, B)) return e;
+  if (B == 0) return 0;
   if (!state || !weights || !reward) return CACTO_E_ARG;
   if (dr_da && !action) return CACTO_E_ARG;
-  if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
 #define M_(SYS) DISPATCH_TL(SYS, launch_reward, *p, weights, state, action, ur5_plain_ucost, reward, dr_da, B, st)
   CACTO_FOR_SYSTEM(p->system, M_)

@@ -1,0 +1,189 @@
+// mlp.cuh -- CTA-level building blocks of the actor / critic kernels (K1 rollout, K3 update).
+//
+// Data layout: a CTA owns a tile of S samples (rollouts or minibatch rows).  Activations of the tile
+// live in shared memory, row-major [S][ld] with ld % 4 == 0; weights are streamed from global memory
+// (they total < 400 KB for both networks and stay L2-resident) straight into registers as float4 --
+// consecutive threads read consecutive 16-byte column groups of a weight row, so every weight load
+// is fully coalesced and every activation load is a shared-memory broadcast.
+//
+//   tile_gemm      C[S x N]  = A[S x K] * W[K x N]        register tile TM x 4 per thread, fp32 FMA
+//   tile_gemm_small C[S x N] = A[S x K] * W                N <= 16 (network heads), K split over lanes
+//   tile_outer2    dW[K x N] += A1^T E1 (+ A2^T E2)        weight gradients, fp32 atomics to global
+//   tile_colsum    db[N]    += sum_s E[s][n]
+//
+// fp32 CUDA-core FMA is used on purpose: the parity gate of this path is 1e-5 (rollout states) /
+// 1e-4 (updated weights) against an fp32 reference, which bf16/tf32 tensor-core products do not
+// meet (SURVEY.md section 7 "Tensor cores vs. parity").
+#pragma once
+#include <cuda_runtime.h>
+#include "mlp_layout.cuh"
+
+namespace cacto {
+
+template <int S, int N, int NT>
+struct GemmMap {
+  static_assert(N % 4 == 0, "N must be a multiple of 4");
+  static constexpr int CG = N / 4;                              // float4 column groups
+  static_assert(CG <= NT && NT % CG == 0, "column groups must tile the CTA");
+  static constexpr int RG = (NT / CG) < S ? (NT / CG) : S;      // row groups in use
+  static_assert(S % RG == 0, "rows must split evenly");
+  static constexpr int TM = S / RG;                             // rows per thread
+};
+
+__device__ __forceinline__ void fma4(float4& acc, float a, const float4& w) {
+  acc.x = fmaf(a, w.x, acc.x);
+  acc.y = fmaf(a, w.y, acc.y);
+  acc.z = fmaf(a, w.z, acc.z);
+  acc.w = fmaf(a, w.w, acc.w);
+}
+
+// C = A * W.  A: shared [S][lda]; W: global, row k at W + k*ldw (ldw % 4 == 0, 16-byte aligned).
+// epi(row, col, acc4) is called once per (row, 4-column group) owned by the thread.
+// The caller synchronises (A must be complete before the call; the epilogue may overwrite A only
+// after a __syncthreads() placed by the caller -- see the `sync_before_epilogue` flag).
+template <int S, int N, int NT, bool SYNC_BEFORE_EPI, typename Epi>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, int K, const float* __restrict__ W, int ldw,
+                                          Epi&& epi) {
+  typedef GemmMap<S, N, NT> M;
+  constexpr int TM = M::TM;
+  const int cg = threadIdx.x % M::CG, rg = threadIdx.x / M::CG;
+  const bool active = rg < M::RG;
+  float4 acc[TM];
+#pragma unroll
+  for (int r = 0; r < TM; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const float* a0 = A + (size_t)(rg * TM) * lda;
+    const float4* wp = reinterpret_cast<const float4*>(W) + cg;
+    const int ldw4 = ldw >> 2;
+    const int K4 = K & ~3;
+    float4 w[4], wn[4];
+    if (K4 > 0) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(wp + (size_t)kk * ldw4);
+    }
+    for (int k = 0; k < K4; k += 4) {
+      if (k + 4 < K4) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) wn[kk] = __ldg(wp + (size_t)(k + 4 + kk) * ldw4);
+      }
+#pragma unroll
+      for (int r = 0; r < TM; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(a0 + r * lda + k);
+        fma4(acc[r], a.x, w[0]);
+        fma4(acc[r], a.y, w[1]);
+        fma4(acc[r], a.z, w[2]);
+        fma4(acc[r], a.w, w[3]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) w[kk] = wn[kk];
+    }
+    for (int k = K4; k < K; ++k) {
+      const float4 wk = __ldg(wp + (size_t)k * ldw4);
+#pragma unroll
+      for (int r = 0; r < TM; ++r) fma4(acc[r], a0[r * lda + k], wk);
+    }
+  }
+  if (SYNC_BEFORE_EPI) __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < TM; ++r) epi(rg * TM + r, 4 * cg, acc[r]);
+  }
+}
+
+// C[s][j] = sum_k A[s][k] * w(k, j) for tiny N.  W_KN: w(k, j) = W[k*N + j]; otherwise w(k, j) = W[j*ldw + k]
+// (rows of a [N x K] matrix).  G lanes cooperate on one output.  epi(row, j, value).
+template <int S, int NT, int G, bool W_KN, typename Epi>
+__device__ __forceinline__ void tile_gemm_small(const float* __restrict__ A, int lda, int K, const float* __restrict__ W, int N,
+                                                int ldw, Epi&& epi) {
+  static_assert(G <= 32 && (G & (G - 1)) == 0, "G must be a power of two <= 32");
+  const int sub = threadIdx.x % G, grp = threadIdx.x / G;
+  constexpr int GROUPS = NT / G;
+  const int total = S * N;
+  for (int base = 0; base < total; base += GROUPS) {
+    const int o = base + grp;
+    const bool valid = o < total;
+    const int s = valid ? o / N : 0, j = valid ? o - (o / N) * N : 0;
+    float acc = 0.f;
+    if (valid) {
+      for (int k = sub; k < K; k += G) {
+        const float w = W_KN ? __ldg(W + (size_t)k * N + j) : __ldg(W + (size_t)j * ldw + k);
+        acc = fmaf(A[s * lda + k], w, acc);
+      }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (valid && sub == 0) epi(s, j, acc);
+  }
+}
+
+// dW[k][n] += scale-free sum_s A1[s][k] E1[s][n] (+ A2[s][k] E2[s][n]); K x N outputs, atomics to global.
+// A*: shared [S][lda*] (k contiguous), E*: shared [S][lde*].  Rows k >= K are skipped.  KT = 4.
+template <int S, int N, int NT>
+__device__ __forceinline__ void tile_outer2(const float* __restrict__ A1, int lda1, const float* __restrict__ E1, int lde1,
+                                            const float* __restrict__ A2, int lda2, const float* __restrict__ E2, int lde2, int K,
+                                            float* __restrict__ dW, int rows_valid) {
+  static_assert(N % 4 == 0, "N % 4");
+  constexpr int CG = N / 4;
+  const int ktiles = (K + 3) >> 2;
+  for (int t = threadIdx.x; t < ktiles * CG; t += NT) {
+    const int cg = t % CG, k0 = (t / CG) << 2;
+    float4 acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < rows_valid; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(A1 + s * lda1 + k0);
+      const float4 e = *reinterpret_cast<const float4*>(E1 + s * lde1 + 4 * cg);
+      fma4(acc[0], a.x, e);
+      fma4(acc[1], a.y, e);
+      fma4(acc[2], a.z, e);
+      fma4(acc[3], a.w, e);
+    }
+    if (A2 != nullptr) {
+      for (int s = 0; s < rows_valid; ++s) {
+        const float4 a = *reinterpret_cast<const float4*>(A2 + s * lda2 + k0);
+        const float4 e = *reinterpret_cast<const float4*>(E2 + s * lde2 + 4 * cg);
+        fma4(acc[0], a.x, e);
+        fma4(acc[1], a.y, e);
+        fma4(acc[2], a.z, e);
+        fma4(acc[3], a.w, e);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (k0 + i < K) {
+        float* d = dW + (size_t)(k0 + i) * N + 4 * cg;
+        atomicAdd(d + 0, acc[i].x);
+        atomicAdd(d + 1, acc[i].y);
+        atomicAdd(d + 2, acc[i].z);
+        atomicAdd(d + 3, acc[i].w);
+      }
+    }
+  }
+}
+
+// db[n] += sum_s E[s][n]
+template <int NT>
+__device__ __forceinline__ void tile_colsum(const float* __restrict__ E, int lde, int N, int rows_valid, float* __restrict__ db) {
+  for (int n = threadIdx.x; n < N; n += NT) {
+    float acc = 0.f;
+    for (int s = 0; s < rows_valid; ++s) acc += E[s * lde + n];
+    atomicAdd(db + n, acc);
+  }
+}
+
+// utils.py:17-24 -- x / norm for the state part, 2 t / T - 1 for the time (last) component.
+__device__ __forceinline__ float normalize_component(const cacto_sys_params& P, int j, float x) {
+  if (!P.normalize) return x;
+  const float n = (float)P.state_norm[j];
+  return (j == P.ns - 1) ? (x / n) * 2.f - 1.f : x / n;
+}
+// d normalised_j / d raw_j
+__device__ __forceinline__ float normalize_scale(const cacto_sys_params& P, int j) {
+  if (!P.normalize) return 1.f;
+  const float n = (float)P.state_norm[j];
+  return (j == P.ns - 1) ? 2.f / n : 1.f / n;
+}
+
+__device__ __forceinline__ float leaky(float z) { return z > 0.f ? z : LEAKY_ALPHA * z; }
+
+}  // namespace cacto

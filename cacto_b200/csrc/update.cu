@@ -1,0 +1,758 @@
+// update.cu -- K3: the Sobolev critic / actor update of RL_AC.update (RL.py:101-118):
+//   k_critic_grad   NN.compute_critic_grad (NeuralNetwork.py:150-178): TD(n) target from the target
+//                   critic, forward F, input-gradient sweep G, Sobolev loss with the signed-log, adjoint
+//                   sweep A through G (the second-order part) and backward sweep B, all for one tile of
+//                   samples without leaving shared memory;
+//   k_actor_grad    NN.compute_actor_grad (NeuralNetwork.py:180-232): actor forward, Env.simulate_batch,
+//                   Env.derivative_batch and d reward_batch/da per sample, critic F+G at s', dQ/da, actor
+//                   backward;
+//   k_adam          tf.keras.optimizers.Adam step (TF 2.11: eps outside the bias correction) fused with the
+//                   Polyak target update (RL.py:113-118), the refresh of the transposed weight copy used
+//                   by the backward sweeps, and the zeroing of the gradient buffer;
+//   k_*_forward     NN.eval for batches (NeuralNetwork.py:130-138).
+// Weight gradients are accumulated with fp32 atomics into one buffer per network (what the NCCL
+// all-reduce of the data-parallel path sums across GPUs).
+#include "common.cuh"
+#include "mlp.cuh"
+#include "systems.cuh"
+
+namespace cacto {
+
+constexpr int UP_NT = 256;
+constexpr int NSP = 16;   // padded state width in shared memory
+constexpr int NAP = 8;    // padded action width
+constexpr int CW = CR_H1 + CR_H2 + CR_H3 + CR_H4;   // 384 hidden units of the critic
+// column offset of hidden layer l inside the [S][CW] activation arrays
+__host__ __device__ __forceinline__ constexpr int koff(int l) { return l == 0 ? 0 : (l == 1 ? CR_H1 : (l == 2 ? CR_H1 + CR_H2 : CR_H1 + CR_H2 + CR_H3)); }
+
+// custom_logarithm (NeuralNetwork.py:140-148) and its TensorFlow gradient (quirk Q10).
+__device__ __forceinline__ float slog(float x) { return x > 0.f ? logf(fmaxf(x, 1e-7f) + 1.f) : -logf(fmaxf(-x, 1e-7f) + 1.f); }
+__device__ __forceinline__ float slog_grad(float x) { return fabsf(x) >= 1e-7f ? 1.f / (fabsf(x) + 1.f) : 0.f; }
+
+// Load `rows` rows of a [B][ns] float state block, normalise (utils.py:17-24) and zero-pad to [S][NSP].
+template <int S>
+__device__ __forceinline__ void load_normalised(const cacto_sys_params& P, const float* __restrict__ g, int64_t row0, int rows,
+                                                float (*X)[NSP]) {
+  const int ns = P.ns;
+  for (int i = threadIdx.x; i < S * NSP; i += UP_NT) {
+    const int s = i / NSP, j = i - s * NSP;
+    float v = 0.f;
+    if (s < rows && j < ns) v = normalize_component(P, j, g[(row0 + s) * ns + j]);
+    X[s][j] = v;
+  }
+}
+
+// Forward pass of the sine critic for a tile, activations ping-ponging between two [S][ld] scratch
+// buffers (>= 128 columns used).  V[s] receives the value.  Ends with a __syncthreads().
+template <int S>
+__device__ __forceinline__ void critic_forward_tile(const float* __restrict__ cw, const CriticLayout& L, const float (*XN)[NSP],
+                                                    float* bufA, float* bufB, int ld, float* V) {
+  tile_gemm<S, CR_H1, UP_NT, false>(&XN[0][0], NSP, L.ns, cw + L.W[0], CR_H1, [&](int r, int c, const float4& a) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[0] + c));
+    *reinterpret_cast<float4*>(bufA + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
+  });
+  __syncthreads();
+  tile_gemm<S, CR_H2, UP_NT, false>(bufA, ld, CR_H1, cw + L.W[1], CR_H2, [&](int r, int c, const float4& a) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[1] + c));
+    *reinterpret_cast<float4*>(bufB + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
+  });
+  __syncthreads();
+  tile_gemm<S, CR_H3, UP_NT, false>(bufB, ld, CR_H2, cw + L.W[2], CR_H3, [&](int r, int c, const float4& a) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[2] + c));
+    *reinterpret_cast<float4*>(bufA + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
+  });
+  __syncthreads();
+  tile_gemm<S, CR_H4, UP_NT, false>(bufA, ld, CR_H3, cw + L.W[3], CR_H4, [&](int r, int c, const float4& a) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[3] + c));
+    *reinterpret_cast<float4*>(bufB + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
+  });
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, true>(bufB, ld, CR_H4, cw + L.W[4], 1, 0, [&](int s, int, float v) { V[s] = v + __ldg(cw + L.b[4]); });
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------ critic
+template <int S>
+struct CriticSmem {
+  float XN[S][NSP], XNN[S][NSP], A0[S][NSP], G0[S][NSP];
+  float SN[S][CW], CS[S][CW], G[S][CW], DL[S][CW], A[S][CW];
+  float V[S], VT[S], VTN[S], Y[S], VBAR[S], WGT[S];
+  float loss;
+};
+
+template <int S>
+__global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ cacto_sys_params P, const float* __restrict__ cw,
+                                                       const float* __restrict__ cwT, const float* __restrict__ tw, float w_S, int mc,
+                                                       const float* __restrict__ state, const float* __restrict__ state_next,
+                                                       const float* __restrict__ prtg, const float* __restrict__ dVdx,
+                                                       const float* __restrict__ done, const float* __restrict__ weights, float inv_B,
+                                                       float* __restrict__ grad, float* __restrict__ rtg_out, float* __restrict__ V_out,
+                                                       float* __restrict__ Vt_out, float* __restrict__ loss_out, int64_t B) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CriticSmem<S>& sm = *reinterpret_cast<CriticSmem<S>*>(smem_raw);
+  const CriticLayout L(P.ns);
+  const int ns = P.ns, nx = P.nx, tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * S;
+  const int rows = (int)min((int64_t)S, B - row0);
+  const bool sobolev = (w_S != 0.f);
+
+  load_normalised<S>(P, state, row0, rows, sm.XN);
+  if (!mc) load_normalised<S>(P, state_next, row0, rows, sm.XNN);
+  if (tid == 0) sm.loss = 0.f;
+  __syncthreads();
+
+  // ---- target critic: V_t(s_next) for the TD(n) tail (NeuralNetwork.py:157-158) and V_t(s) (:178)
+  if (!mc) critic_forward_tile<S>(tw, L, sm.XNN, &sm.A[0][0], &sm.DL[0][0], CW, sm.VTN);
+  critic_forward_tile<S>(tw, L, sm.XN, &sm.A[0][0], &sm.DL[0][0], CW, sm.VT);
+  if (tid < S) {
+    float y = 0.f, w = 0.f;
+    if (tid < rows) {
+      const int64_t b = row0 + tid;
+      y = mc ? prtg[b] : prtg[b] + (1.f - done[b]) * sm.VTN[tid];
+      w = weights[b];
+      rtg_out[b] = y;
+      Vt_out[b] = sm.VT[tid];
+    }
+    sm.Y[tid] = y;
+    sm.WGT[tid] = w;
+  }
+
+  // ---- F: forward, keeping sin z_l and cos z_l of every hidden layer
+  auto f_epi = [&](int l) {
+    return [&, l](int r, int c, const float4& a) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[l] + c));
+      float4 s, co;
+      sincosf(a.x + b.x, &s.x, &co.x);
+      sincosf(a.y + b.y, &s.y, &co.y);
+      sincosf(a.z + b.z, &s.z, &co.z);
+      sincosf(a.w + b.w, &s.w, &co.w);
+      *reinterpret_cast<float4*>(&sm.SN[r][koff(l) + c]) = s;
+      *reinterpret_cast<float4*>(&sm.CS[r][koff(l) + c]) = co;
+    };
+  };
+  tile_gemm<S, CR_H1, UP_NT, false>(&sm.XN[0][0], NSP, ns, cw + L.W[0], CR_H1, f_epi(0));
+  __syncthreads();
+  tile_gemm<S, CR_H2, UP_NT, false>(&sm.SN[0][koff(0)], CW, CR_H1, cw + L.W[1], CR_H2, f_epi(1));
+  __syncthreads();
+  tile_gemm<S, CR_H3, UP_NT, false>(&sm.SN[0][koff(1)], CW, CR_H2, cw + L.W[2], CR_H3, f_epi(2));
+  __syncthreads();
+  tile_gemm<S, CR_H4, UP_NT, false>(&sm.SN[0][koff(2)], CW, CR_H3, cw + L.W[3], CR_H4, f_epi(3));
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, true>(&sm.SN[0][koff(3)], CW, CR_H4, cw + L.W[4], 1, 0,
+                                     [&](int s, int, float v) { sm.V[s] = v + __ldg(cw + L.b[4]); });
+  __syncthreads();
+  if (tid < rows) V_out[row0 + tid] = sm.V[tid];
+
+  if (sobolev) {
+    // ---- G: dV/dx through the network (tape2 of NeuralNetwork.py:162-165)
+    for (int i = tid; i < S * CR_H4; i += UP_NT) {
+      const int s = i / CR_H4, o = i - s * CR_H4;
+      const float w5 = __ldg(cw + L.W[4] + o);
+      sm.G[s][koff(3) + o] = w5;
+      sm.DL[s][koff(3) + o] = w5 * sm.CS[s][koff(3) + o];
+    }
+    __syncthreads();
+    auto g_epi = [&](int l) {
+      return [&, l](int r, int c, const float4& a) {
+        const float4 co = *reinterpret_cast<const float4*>(&sm.CS[r][koff(l) + c]);
+        *reinterpret_cast<float4*>(&sm.G[r][koff(l) + c]) = a;
+        *reinterpret_cast<float4*>(&sm.DL[r][koff(l) + c]) = make_float4(a.x * co.x, a.y * co.y, a.z * co.z, a.w * co.w);
+      };
+    };
+    tile_gemm<S, CR_H3, UP_NT, false>(&sm.DL[0][koff(3)], CW, CR_H4, cwT + L.W[3], CR_H3, g_epi(2));
+    __syncthreads();
+    tile_gemm<S, CR_H2, UP_NT, false>(&sm.DL[0][koff(2)], CW, CR_H3, cwT + L.W[2], CR_H2, g_epi(1));
+    __syncthreads();
+    tile_gemm<S, CR_H1, UP_NT, false>(&sm.DL[0][koff(1)], CW, CR_H2, cwT + L.W[1], CR_H1, g_epi(0));
+    __syncthreads();
+    tile_gemm_small<S, UP_NT, 8, false>(&sm.DL[0][koff(0)], CW, CR_H1, cw + L.W[0], ns, CR_H1,
+                                        [&](int s, int j, float v) { sm.G0[s][j] = v; });
+    __syncthreads();
+  }
+
+  // ---- loss and its seeds (NeuralNetwork.py:167-173)
+  {
+    float lsum = 0.f;
+    if (sobolev) {
+      for (int i = tid; i < S * NSP; i += UP_NT) {
+        const int s = i / NSP, j = i - s * NSP;
+        float a0 = 0.f;
+        if (s < rows && j < nx) {
+          const float D = normalize_scale(P, j);
+          const float gs = D * sm.G0[s][j];
+          const float diff = slog(dVdx[(row0 + s) * ns + j]) - slog(gs);
+          const float wn = sm.WGT[s] * inv_B / (float)nx;
+          a0 = D * (-2.f * wn * diff * slog_grad(gs));
+          lsum += wn * diff * diff;
+        }
+        sm.A0[s][j] = a0;
+      }
+    }
+    if (tid < S) {
+      float vbar = 0.f;
+      if (tid < rows) {
+        const float e = sm.Y[tid] - sm.V[tid];
+        const float k = sobolev ? w_S : 1.f;
+        vbar = -2.f * sm.WGT[tid] * k * inv_B * e;
+        lsum += sm.WGT[tid] * k * inv_B * e * e;
+      }
+      sm.VBAR[tid] = vbar;
+    }
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if ((tid & 31) == 0 && lsum != 0.f) atomicAdd(&sm.loss, lsum);
+  }
+  __syncthreads();
+  if (tid == 0 && loss_out != nullptr) atomicAdd(loss_out, sm.loss);
+
+  if (sobolev) {
+    // ---- A: adjoint sweep through G (second-order terms); extra_l overwrites g_l, a_l kept for the outer products
+    auto a_epi = [&](int l) {
+      return [&, l](int r, int c, const float4& t) {
+        const float4 co = *reinterpret_cast<const float4*>(&sm.CS[r][koff(l) + c]);
+        const float4 si = *reinterpret_cast<const float4*>(&sm.SN[r][koff(l) + c]);
+        const float4 g = *reinterpret_cast<const float4*>(&sm.G[r][koff(l) + c]);
+        *reinterpret_cast<float4*>(&sm.A[r][koff(l) + c]) = make_float4(t.x * co.x, t.y * co.y, t.z * co.z, t.w * co.w);
+        *reinterpret_cast<float4*>(&sm.G[r][koff(l) + c]) =
+            make_float4(-t.x * g.x * si.x, -t.y * g.y * si.y, -t.z * g.z * si.z, -t.w * g.w * si.w);
+      };
+    };
+    tile_gemm<S, CR_H1, UP_NT, false>(&sm.A0[0][0], NSP, ns, cw + L.W[0], CR_H1, a_epi(0));
+    __syncthreads();
+    tile_gemm<S, CR_H2, UP_NT, false>(&sm.A[0][koff(0)], CW, CR_H1, cw + L.W[1], CR_H2, a_epi(1));
+    __syncthreads();
+    tile_gemm<S, CR_H3, UP_NT, false>(&sm.A[0][koff(1)], CW, CR_H2, cw + L.W[2], CR_H3, a_epi(2));
+    __syncthreads();
+    tile_gemm<S, CR_H4, UP_NT, false>(&sm.A[0][koff(2)], CW, CR_H3, cw + L.W[3], CR_H4, a_epi(3));
+    __syncthreads();
+    tile_colsum<UP_NT>(&sm.A[0][koff(3)], CW, CR_H4, rows, grad + L.W[4]);       // d w5 += sum_s a_4
+  } else {
+    for (int i = tid; i < S * CW; i += UP_NT) sm.G[i / CW][i % CW] = 0.f;
+    __syncthreads();
+  }
+
+  // ---- B: ordinary backward through F with the injected second-order terms
+  for (int i = tid; i < S * CR_H4; i += UP_NT) {
+    const int s = i / CR_H4, o = i - s * CR_H4;
+    sm.G[s][koff(3) + o] += sm.VBAR[s] * __ldg(cw + L.W[4] + o) * sm.CS[s][koff(3) + o];      // e_4
+  }
+  for (int o = tid; o < CR_H4; o += UP_NT) {                                                   // d w5 += sum_s vbar h_4
+    float acc = 0.f;
+    for (int s = 0; s < rows; ++s) acc += sm.VBAR[s] * sm.SN[s][koff(3) + o];
+    atomicAdd(grad + L.W[4] + o, acc);
+  }
+  if (tid == 0) {
+    float acc = 0.f;
+    for (int s = 0; s < rows; ++s) acc += sm.VBAR[s];
+    atomicAdd(grad + L.b[4], acc);
+  }
+  __syncthreads();
+  auto b_epi = [&](int l) {   // e_l = (e_{l+1} W_{l+1}^T) * cos z_l + extra_l
+    return [&, l](int r, int c, const float4& hb) {
+      const float4 co = *reinterpret_cast<const float4*>(&sm.CS[r][koff(l) + c]);
+      float4 g = *reinterpret_cast<const float4*>(&sm.G[r][koff(l) + c]);
+      g.x += hb.x * co.x; g.y += hb.y * co.y; g.z += hb.z * co.z; g.w += hb.w * co.w;
+      *reinterpret_cast<float4*>(&sm.G[r][koff(l) + c]) = g;
+    };
+  };
+  const float* A2 = sobolev ? &sm.A[0][0] : nullptr;
+  // layer 4
+  tile_outer2<S, CR_H4, UP_NT>(&sm.SN[0][koff(2)], CW, &sm.G[0][koff(3)], CW, A2 ? A2 + koff(2) : nullptr, CW, &sm.DL[0][koff(3)], CW,
+                               CR_H3, grad + L.W[3], rows);
+  tile_colsum<UP_NT>(&sm.G[0][koff(3)], CW, CR_H4, rows, grad + L.b[3]);
+  tile_gemm<S, CR_H3, UP_NT, false>(&sm.G[0][koff(3)], CW, CR_H4, cwT + L.W[3], CR_H3, b_epi(2));
+  __syncthreads();
+  // layer 3
+  tile_outer2<S, CR_H3, UP_NT>(&sm.SN[0][koff(1)], CW, &sm.G[0][koff(2)], CW, A2 ? A2 + koff(1) : nullptr, CW, &sm.DL[0][koff(2)], CW,
+                               CR_H2, grad + L.W[2], rows);
+  tile_colsum<UP_NT>(&sm.G[0][koff(2)], CW, CR_H3, rows, grad + L.b[2]);
+  tile_gemm<S, CR_H2, UP_NT, false>(&sm.G[0][koff(2)], CW, CR_H3, cwT + L.W[2], CR_H2, b_epi(1));
+  __syncthreads();
+  // layer 2
+  tile_outer2<S, CR_H2, UP_NT>(&sm.SN[0][koff(0)], CW, &sm.G[0][koff(1)], CW, A2 ? A2 + koff(0) : nullptr, CW, &sm.DL[0][koff(1)], CW,
+                               CR_H1, grad + L.W[1], rows);
+  tile_colsum<UP_NT>(&sm.G[0][koff(1)], CW, CR_H2, rows, grad + L.b[1]);
+  tile_gemm<S, CR_H1, UP_NT, false>(&sm.G[0][koff(1)], CW, CR_H2, cwT + L.W[1], CR_H1, b_epi(0));
+  __syncthreads();
+  // layer 1
+  tile_outer2<S, CR_H1, UP_NT>(&sm.XN[0][0], NSP, &sm.G[0][koff(0)], CW, sobolev ? &sm.A0[0][0] : nullptr, NSP, &sm.DL[0][koff(0)], CW, ns,
+                               grad + L.W[0], rows);
+  tile_colsum<UP_NT>(&sm.G[0][koff(0)], CW, CR_H1, rows, grad + L.b[0]);
+}
+
+// ------------------------------------------------------------------------------------------ actor
+template <int S>
+struct ActorSmem {
+  float XN[S][NSP], XNP[S][NSP], G0[S][NSP];
+  float H1[S][ACTOR_H], H2[S][ACTOR_H], E[S][ACTOR_H];
+  float CS[S][CW];
+  float CH[2][S][CR_H4];
+  float DLp[2][S][CR_H4];
+  float FU[S][CACTO_MAX_NS * CACTO_MAX_NA + 2];
+  float ACT[S][NAP], D3[S][NAP], DRDA[S][NAP];
+};
+
+template <int SYS, int S>
+__global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ cacto_sys_params P, const float* __restrict__ aw,
+                                                      const float* __restrict__ awT, const float* __restrict__ cw,
+                                                      const float* __restrict__ cwT, const float* __restrict__ state,
+                                                      const double* __restrict__ term, float inv_B, float* __restrict__ grad,
+                                                      float* __restrict__ actions_out, int64_t B) {
+  constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA, NS = NX + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ActorSmem<S>& sm = *reinterpret_cast<ActorSmem<S>*>(smem_raw);
+  const ActorLayout LA(NS, NA);
+  const CriticLayout LC(NS);
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * S;
+  const int rows = (int)min((int64_t)S, B - row0);
+
+  load_normalised<S>(P, state, row0, rows, sm.XN);
+  __syncthreads();
+  // ---- actor forward (NeuralNetwork.py:185)
+  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.XN[0][0], NSP, NS, aw + LA.W1, ACTOR_H, [&](int r, int c, const float4& a) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(aw + LA.b1 + c));
+    *reinterpret_cast<float4*>(&sm.H1[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
+  });
+  __syncthreads();
+  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.H1[0][0], ACTOR_H, ACTOR_H, aw + LA.W2, ACTOR_H, [&](int r, int c, const float4& a) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(aw + LA.b2 + c));
+    *reinterpret_cast<float4*>(&sm.H2[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
+  });
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, true>(&sm.H2[0][0], ACTOR_H, ACTOR_H, aw + LA.W3, NA, 0,
+                                     [&](int s, int j, float v) { sm.ACT[s][j] = v + __ldg(aw + LA.b3 + j); });
+  __syncthreads();
+
+  // ---- per sample: s' = f(s, a), ds'/da (normalised), dr/da  (NeuralNetwork.py:188,199-204)
+  if (tid < S) {
+    float xnp[NSP];
+#pragma unroll
+    for (int j = 0; j < NSP; ++j) xnp[j] = 0.f;
+    if (tid < rows) {
+      const int64_t b = row0 + tid;
+      double x[NS], u[NA], xn[NS], Fu[NX * NA];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) x[j] = (double)state[b * NS + j];
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        u[j] = (double)sm.ACT[tid][j];
+        if (actions_out != nullptr) actions_out[b * NA + j] = sm.ACT[tid][j];
+      }
+      sys_step<SYS, double>(P, x, u, xn);
+      xn[NX] = x[NX] + P.dt;
+      sys_Fu<SYS, double>(P, x, Fu);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const double inv = P.normalize ? 1.0 / P.state_norm[i] : 1.0;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) sm.FU[tid][i * NA + j] = (float)(Fu[i * NA + j] * inv);
+      }
+#pragma unroll
+      for (int j = 0; j < NA; ++j) sm.FU[tid][NX * NA + j] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) xnp[j] = normalize_component(P, j, (float)xn[j]);
+      const double tm = term[b];
+      const float w6 = (float)(tm * P.w_terminal[6] + (1.0 - tm) * P.w_running[6]);     // NeuralNetwork.py:201
+      float uf[NA], g[NA];
+#pragma unroll
+      for (int j = 0; j < NA; ++j) uf[j] = sm.ACT[tid][j];
+      sys_dr_da<SYS, float>(P, w6, uf, g);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) sm.DRDA[tid][j] = g[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NSP; ++j) sm.XNP[tid][j] = xnp[j];
+  }
+  __syncthreads();
+
+  // ---- critic forward at s' keeping cos z_l, then the input-gradient sweep (NeuralNetwork.py:190-195)
+  auto cf_epi = [&](int l, float* out) {
+    return [&, l, out](int r, int c, const float4& a) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(cw + LC.b[l] + c));
+      float4 s, co;
+      sincosf(a.x + b.x, &s.x, &co.x);
+      sincosf(a.y + b.y, &s.y, &co.y);
+      sincosf(a.z + b.z, &s.z, &co.z);
+      sincosf(a.w + b.w, &s.w, &co.w);
+      *reinterpret_cast<float4*>(out + r * CR_H4 + c) = s;
+      *reinterpret_cast<float4*>(&sm.CS[r][koff(l) + c]) = co;
+    };
+  };
+  float* ch0 = &sm.CH[0][0][0];
+  float* ch1 = &sm.CH[1][0][0];
+  tile_gemm<S, CR_H1, UP_NT, false>(&sm.XNP[0][0], NSP, NS, cw + LC.W[0], CR_H1, cf_epi(0, ch0));
+  __syncthreads();
+  tile_gemm<S, CR_H2, UP_NT, false>(ch0, CR_H4, CR_H1, cw + LC.W[1], CR_H2, cf_epi(1, ch1));
+  __syncthreads();
+  tile_gemm<S, CR_H3, UP_NT, false>(ch1, CR_H4, CR_H2, cw + LC.W[2], CR_H3, cf_epi(2, ch0));
+  __syncthreads();
+  tile_gemm<S, CR_H4, UP_NT, false>(ch0, CR_H4, CR_H3, cw + LC.W[3], CR_H4, cf_epi(3, ch1));
+  __syncthreads();
+  float* dl0 = &sm.DLp[0][0][0];
+  float* dl1 = &sm.DLp[1][0][0];
+  for (int i = tid; i < S * CR_H4; i += UP_NT) {
+    const int s = i / CR_H4, o = i - s * CR_H4;
+    dl0[s * CR_H4 + o] = __ldg(cw + LC.W[4] + o) * sm.CS[s][koff(3) + o];
+  }
+  __syncthreads();
+  auto cg_epi = [&](int l, float* out) {
+    return [&, l, out](int r, int c, const float4& a) {
+      const float4 co = *reinterpret_cast<const float4*>(&sm.CS[r][koff(l) + c]);
+      *reinterpret_cast<float4*>(out + r * CR_H4 + c) = make_float4(a.x * co.x, a.y * co.y, a.z * co.z, a.w * co.w);
+    };
+  };
+  tile_gemm<S, CR_H3, UP_NT, false>(dl0, CR_H4, CR_H4, cwT + LC.W[3], CR_H3, cg_epi(2, dl1));
+  __syncthreads();
+  tile_gemm<S, CR_H2, UP_NT, false>(dl1, CR_H4, CR_H3, cwT + LC.W[2], CR_H2, cg_epi(1, dl0));
+  __syncthreads();
+  tile_gemm<S, CR_H1, UP_NT, false>(dl0, CR_H4, CR_H2, cwT + LC.W[1], CR_H1, cg_epi(0, dl1));
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, false>(dl1, CR_H4, CR_H1, cw + LC.W[0], NS, CR_H1, [&](int s, int j, float v) { sm.G0[s][j] = v; });
+  __syncthreads();
+
+  // ---- dQ/da = dV/ds' . ds'/da + dr/da ; upstream gradient on the actor output = -dQ/da / B  (:206-228)
+  for (int i = tid; i < S * NAP; i += UP_NT) {
+    const int s = i / NAP, j = i - s * NAP;
+    float d3 = 0.f;
+    if (s < rows && j < NA) {
+      float q = sm.DRDA[s][j];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) q = fmaf(normalize_scale(P, k) * sm.G0[s][k], sm.FU[s][k * NA + j], q);
+      d3 = -q * inv_B;
+    }
+    sm.D3[s][j] = d3;
+  }
+  __syncthreads();
+
+  // ---- actor backward
+  for (int i = tid; i < ACTOR_H * NA; i += UP_NT) {            // dW3[k][j] += sum_s h2[s][k] d3[s][j]
+    const int k = i / NA, j = i - k * NA;
+    float acc = 0.f;
+    for (int s = 0; s < rows; ++s) acc = fmaf(sm.H2[s][k], sm.D3[s][j], acc);
+    atomicAdd(grad + LA.W3 + i, acc);
+  }
+  if (tid < NA) {
+    float acc = 0.f;
+    for (int s = 0; s < rows; ++s) acc += sm.D3[s][tid];
+    atomicAdd(grad + LA.b3 + tid, acc);
+  }
+  for (int i = tid; i < S * ACTOR_H; i += UP_NT) {             // e2 = (d3 W3^T) * lrelu'(z2)
+    const int s = i / ACTOR_H, n = i - s * ACTOR_H;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NA; ++j) acc = fmaf(sm.D3[s][j], __ldg(aw + LA.W3 + n * NA + j), acc);
+    sm.E[s][n] = acc * (sm.H2[s][n] > 0.f ? 1.f : LEAKY_ALPHA);
+  }
+  __syncthreads();
+  tile_outer2<S, ACTOR_H, UP_NT>(&sm.H1[0][0], ACTOR_H, &sm.E[0][0], ACTOR_H, nullptr, 0, nullptr, 0, ACTOR_H, grad + LA.W2, rows);
+  tile_colsum<UP_NT>(&sm.E[0][0], ACTOR_H, ACTOR_H, rows, grad + LA.b2);
+  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.E[0][0], ACTOR_H, ACTOR_H, awT + LA.W2, ACTOR_H, [&](int r, int c, const float4& a) {
+    const float4 h = *reinterpret_cast<const float4*>(&sm.H1[r][c]);
+    *reinterpret_cast<float4*>(&sm.H2[r][c]) =
+        make_float4(a.x * (h.x > 0.f ? 1.f : LEAKY_ALPHA), a.y * (h.y > 0.f ? 1.f : LEAKY_ALPHA), a.z * (h.z > 0.f ? 1.f : LEAKY_ALPHA),
+                    a.w * (h.w > 0.f ? 1.f : LEAKY_ALPHA));
+  });
+  __syncthreads();
+  tile_outer2<S, ACTOR_H, UP_NT>(&sm.XN[0][0], NSP, &sm.H2[0][0], ACTOR_H, nullptr, 0, nullptr, 0, NS, grad + LA.W1, rows);
+  tile_colsum<UP_NT>(&sm.H2[0][0], ACTOR_H, ACTOR_H, rows, grad + LA.b1);
+}
+
+// ------------------------------------------------------------------------------------------ forward-only kernels
+template <int S>
+struct EvalSmem {
+  float XN[S][NSP];
+  float A[S][ACTOR_H], Bf[S][ACTOR_H];
+  float CS[S][CW];
+  float V[S], G0[S][NSP];
+  float ACT[S][NAP];
+};
+
+template <int S>
+__global__ void __launch_bounds__(UP_NT) k_actor_forward(const __grid_constant__ cacto_sys_params P, const float* __restrict__ aw,
+                                                         const float* __restrict__ state, float* __restrict__ out, int64_t B) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EvalSmem<S>& sm = *reinterpret_cast<EvalSmem<S>*>(smem_raw);
+  const int ns = P.ns, na = P.na;
+  const ActorLayout LA(ns, na);
+  const int64_t row0 = (int64_t)blockIdx.x * S;
+  const int rows = (int)min((int64_t)S, B - row0);
+  load_normalised<S>(P, state, row0, rows, sm.XN);
+  __syncthreads();
+  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.XN[0][0], NSP, ns, aw + LA.W1, ACTOR_H, [&](int r, int c, const float4& a) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(aw + LA.b1 + c));
+    *reinterpret_cast<float4*>(&sm.A[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
+  });
+  __syncthreads();
+  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.A[0][0], ACTOR_H, ACTOR_H, aw + LA.W2, ACTOR_H, [&](int r, int c, const float4& a) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(aw + LA.b2 + c));
+    *reinterpret_cast<float4*>(&sm.Bf[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
+  });
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, true>(&sm.Bf[0][0], ACTOR_H, ACTOR_H, aw + LA.W3, na, 0, [&](int s, int j, float v) {
+    if (s < rows) out[(row0 + s) * na + j] = v + __ldg(aw + LA.b3 + j);
+  });
+}
+
+template <int S>
+__global__ void __launch_bounds__(UP_NT) k_critic_forward(const __grid_constant__ cacto_sys_params P, const float* __restrict__ cw,
+                                                          const float* __restrict__ state, float* __restrict__ value,
+                                                          float* __restrict__ dV_ds, int64_t B) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EvalSmem<S>& sm = *reinterpret_cast<EvalSmem<S>*>(smem_raw);
+  const int ns = P.ns, tid = threadIdx.x;
+  const CriticLayout L(ns);
+  const int64_t row0 = (int64_t)blockIdx.x * S;
+  const int rows = (int)min((int64_t)S, B - row0);
+  load_normalised<S>(P, state, row0, rows, sm.XN);
+  __syncthreads();
+  float* bufA = &sm.A[0][0];
+  float* bufB = &sm.Bf[0][0];
+  auto f_epi = [&](int l, float* out) {
+    return [&, l, out](int r, int c, const float4& a) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[l] + c));
+      float4 s, co;
+      sincosf(a.x + b.x, &s.x, &co.x);
+      sincosf(a.y + b.y, &s.y, &co.y);
+      sincosf(a.z + b.z, &s.z, &co.z);
+      sincosf(a.w + b.w, &s.w, &co.w);
+      *reinterpret_cast<float4*>(out + r * ACTOR_H + c) = s;
+      *reinterpret_cast<float4*>(&sm.CS[r][koff(l) + c]) = co;
+    };
+  };
+  tile_gemm<S, CR_H1, UP_NT, false>(&sm.XN[0][0], NSP, ns, cw + L.W[0], CR_H1, f_epi(0, bufA));
+  __syncthreads();
+  tile_gemm<S, CR_H2, UP_NT, false>(bufA, ACTOR_H, CR_H1, cw + L.W[1], CR_H2, f_epi(1, bufB));
+  __syncthreads();
+  tile_gemm<S, CR_H3, UP_NT, false>(bufB, ACTOR_H, CR_H2, cw + L.W[2], CR_H3, f_epi(2, bufA));
+  __syncthreads();
+  tile_gemm<S, CR_H4, UP_NT, false>(bufA, ACTOR_H, CR_H3, cw + L.W[3], CR_H4, f_epi(3, bufB));
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, true>(bufB, ACTOR_H, CR_H4, cw + L.W[4], 1, 0, [&](int s, int, float v) {
+    if (s < rows) value[row0 + s] = v + __ldg(cw + L.b[4]);
+  });
+  if (dV_ds == nullptr) return;
+  __syncthreads();
+  // input gradient with the un-transposed weights (forward-only callers have no transposed copy):
+  // g_{l-1}[s][i] = sum_o delta_l[s][o] W_l[i][o]  -> G lanes per output over contiguous W rows
+  for (int i = tid; i < S * CR_H4; i += UP_NT) {
+    const int s = i / CR_H4, o = i - s * CR_H4;
+    bufA[s * ACTOR_H + o] = __ldg(cw + L.W[4] + o) * sm.CS[s][koff(3) + o];
+  }
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, false>(bufA, ACTOR_H, CR_H4, cw + L.W[3], CR_H3, CR_H4,
+                                      [&](int s, int j, float v) { bufB[s * ACTOR_H + j] = v * sm.CS[s][koff(2) + j]; });
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, false>(bufB, ACTOR_H, CR_H3, cw + L.W[2], CR_H2, CR_H3,
+                                      [&](int s, int j, float v) { bufA[s * ACTOR_H + j] = v * sm.CS[s][koff(1) + j]; });
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, false>(bufA, ACTOR_H, CR_H2, cw + L.W[1], CR_H1, CR_H2,
+                                      [&](int s, int j, float v) { bufB[s * ACTOR_H + j] = v * sm.CS[s][koff(0) + j]; });
+  __syncthreads();
+  tile_gemm_small<S, UP_NT, 8, false>(bufB, ACTOR_H, CR_H1, cw + L.W[0], ns, CR_H1, [&](int s, int j, float v) {
+    if (s < rows) dV_ds[(row0 + s) * ns + j] = normalize_scale(P, j) * v;
+  });
+}
+
+// ------------------------------------------------------------------------------------------ optimiser
+struct LayerTable {
+  int n;
+  int64_t W[5];
+  int in[5], out[5];
+};
+
+// p -= alpha * m / (sqrt(v) + eps) with m += (g - m)(1 - b1), v += (g^2 - v)(1 - b2)   
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                              float alpha, float omb1, float omb2, float eps, float* __restrict__ target, float tau,
+                                              float* __restrict__ pT, LayerTable T, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  g[i] = 0.f;
+  float mi = m[i], vi = v[i];
+  mi += (gi - mi) * omb1;
+  vi += (gi * gi - vi) * omb2;
+  m[i] = mi;
+  v[i] = vi;
+  const float pi = p[i] - (mi * alpha) / (sqrtf(vi) + eps);
+  p[i] = pi;
+  if (target != nullptr) target[i] = pi * tau + target[i] * (1.f - tau);      // RL.py:116-118
+  if (pT != nullptr) {
+    int64_t j = i;
+    for (int l = 0; l < T.n; ++l) {
+      const int64_t sz = (int64_t)T.in[l] * T.out[l];
+      if (i >= T.W[l] && i < T.W[l] + sz) {
+        const int64_t e = i - T.W[l];
+        const int r = (int)(e / T.out[l]), c = (int)(e - (int64_t)r * T.out[l]);
+        j = T.W[l] + (int64_t)c * T.in[l] + r;
+        break;
+      }
+    }
+    pT[j] = pi;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_transpose(const float* __restrict__ p, float* __restrict__ pT, LayerTable T, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t j = i;
+  for (int l = 0; l < T.n; ++l) {
+    const int64_t sz = (int64_t)T.in[l] * T.out[l];
+    if (i >= T.W[l] && i < T.W[l] + sz) {
+      const int64_t e = i - T.W[l];
+      const int r = (int)(e / T.out[l]), c = (int)(e - (int64_t)r * T.out[l]);
+      j = T.W[l] + (int64_t)c * T.in[l] + r;
+      break;
+    }
+  }
+  pT[j] = p[i];
+}
+
+static LayerTable make_table(int is_critic, int ns, int na, int64_t* total) {
+  LayerTable T;
+  if (is_critic) {
+    CriticLayout L(ns);
+    T.n = 5;
+    for (int l = 0; l < 5; ++l) { T.W[l] = L.W[l]; T.in[l] = L.in[l]; T.out[l] = L.out[l]; }
+    *total = L.total;
+  } else {
+    ActorLayout L(ns, na);
+    T.n = 3;
+    T.W[0] = L.W1; T.in[0] = ns; T.out[0] = ACTOR_H;
+    T.W[1] = L.W2; T.in[1] = ACTOR_H; T.out[1] = ACTOR_H;
+    T.W[2] = L.W3; T.in[2] = ACTOR_H; T.out[2] = na;
+    for (int l = 3; l < 5; ++l) { T.W[l] = 0; T.in[l] = 0; T.out[l] = 0; }
+    *total = L.total;
+  }
+  return T;
+}
+
+template <typename K>
+static int smem_attr(K k, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+static int pick_tile(int64_t B) { return B >= 16 * 148 ? 16 : 8; }
+
+template <int SYS>
+static int launch_actor_grad(const cacto_sys_params& P, const float* aw, const float* awT, const float* cw, const float* cwT,
+                             const float* state, const double* term, float inv_B, float* grad, float* actions, int64_t B,
+                             cudaStream_t st) {
+  if (pick_tile(B) == 16) {
+    auto k = k_actor_grad<SYS, 16>;
+    if (int e = smem_attr(k, sizeof(ActorSmem<16>))) return e;
+    k<<<(unsigned)((B + 15) / 16), UP_NT, sizeof(ActorSmem<16>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
+  } else {
+    auto k = k_actor_grad<SYS, 8>;
+    if (int e = smem_attr(k, sizeof(ActorSmem<8>))) return e;
+    k<<<(unsigned)((B + 7) / 8), UP_NT, sizeof(ActorSmem<8>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
+  }
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace cacto
+
+using namespace cacto;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int cacto_critic_grad(const cacto_sys_params* p, const float* critic_params, const float* critic_params_T,
+                                 const float* target_params, float w_S, int mc, const float* state, const float* state_next,
+                                 const float* partial_rtg, const float* dVdx, const float* done, const float* weights, float inv_B,
+                                 float* grad, float* rtg, float* V, float* V_target_s, float* loss, int64_t B, void* stream) {
+  if (!p) return CACTO_E_ARG;
+  if (B < 0) return CACTO_E_SIZE;
+  if (B == 0) return 0;
+  if (!critic_params || !critic_params_T || !target_params || !state || !partial_rtg || !weights || !grad || !rtg || !V || !V_target_s)
+    return CACTO_E_ARG;
+  if (!mc && (!state_next || !done)) return CACTO_E_ARG;
+  if (w_S != 0.f && !dVdx) return CACTO_E_ARG;
+  if (!aligned16(critic_params) || !aligned16(critic_params_T) || !aligned16(target_params)) return CACTO_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pick_tile(B) == 16) {
+    auto k = k_critic_grad<16>;
+    if (int e = smem_attr(k, sizeof(CriticSmem<16>))) return e;
+    k<<<(unsigned)((B + 15) / 16), UP_NT, sizeof(CriticSmem<16>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
+                                                                        state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
+                                                                        V_target_s, loss, B);
+  } else {
+    auto k = k_critic_grad<8>;
+    if (int e = smem_attr(k, sizeof(CriticSmem<8>))) return e;
+    k<<<(unsigned)((B + 7) / 8), UP_NT, sizeof(CriticSmem<8>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
+                                                                     state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
+                                                                     V_target_s, loss, B);
+  }
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_actor_grad(const cacto_sys_params* p, const float* actor_params, const float* actor_params_T,
+                                const float* critic_params, const float* critic_params_T, const float* state, const double* term,
+                                float inv_B, float* grad, float* actions, int64_t B, void* stream) {
+  if (!p) return CACTO_E_ARG;
+  if (B < 0) return CACTO_E_SIZE;
+  if (B == 0) return 0;
+  if (!actor_params || !actor_params_T || !critic_params || !critic_params_T || !state || !term || !grad) return CACTO_E_ARG;
+  if (!aligned16(actor_params) || !aligned16(actor_params_T) || !aligned16(critic_params) || !aligned16(critic_params_T)) return CACTO_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p->system) {
+    case CACTO_SINGLE_INTEGRATOR: return launch_actor_grad<CACTO_SINGLE_INTEGRATOR>(*p, actor_params, actor_params_T, critic_params, critic_params_T, state, term, inv_B, grad, actions, B, st);
+    case CACTO_DOUBLE_INTEGRATOR: return launch_actor_grad<CACTO_DOUBLE_INTEGRATOR>(*p, actor_params, actor_params_T, critic_params, critic_params_T, state, term, inv_B, grad, actions, B, st);
+    case CACTO_CAR: return launch_actor_grad<CACTO_CAR>(*p, actor_params, actor_params_T, critic_params, critic_params_T, state, term, inv_B, grad, actions, B, st);
+    case CACTO_CAR_PARK: return launch_actor_grad<CACTO_CAR_PARK>(*p, actor_params, actor_params_T, critic_params, critic_params_T, state, term, inv_B, grad, actions, B, st);
+    case CACTO_MANIPULATOR: return launch_actor_grad<CACTO_MANIPULATOR>(*p, actor_params, actor_params_T, critic_params, critic_params_T, state, term, inv_B, grad, actions, B, st);
+    case CACTO_UR5: return launch_actor_grad<CACTO_UR5>(*p, actor_params, actor_params_T, critic_params, critic_params_T, state, term, inv_B, grad, actions, B, st);
+    default: return CACTO_E_SYSTEM;
+  }
+}
+
+extern "C" int cacto_actor_forward(const cacto_sys_params* p, const float* actor_params, const float* state, float* out, int64_t B,
+                                   void* stream) {
+  if (!p) return CACTO_E_ARG;
+  if (B < 0) return CACTO_E_SIZE;
+  if (B == 0) return 0;
+  if (!actor_params || !state || !out) return CACTO_E_ARG;
+  if (!aligned16(actor_params)) return CACTO_E_ALIGN;
+  auto k = k_actor_forward<16>;
+  if (int e = smem_attr(k, sizeof(EvalSmem<16>))) return e;
+  k<<<(unsigned)((B + 15) / 16), UP_NT, sizeof(EvalSmem<16>), (cudaStream_t)stream>>>(*p, actor_params, state, out, B);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_critic_forward(const cacto_sys_params* p, const float* critic_params, const float* state, float* value,
+                                    float* dV_ds, int64_t B, void* stream) {
+  if (!p) return CACTO_E_ARG;
+  if (B < 0) return CACTO_E_SIZE;
+  if (B == 0) return 0;
+  if (!critic_params || !state || !value) return CACTO_E_ARG;
+  if (!aligned16(critic_params)) return CACTO_E_ALIGN;
+  auto k = k_critic_forward<16>;
+  if (int e = smem_attr(k, sizeof(EvalSmem<16>))) return e;
+  k<<<(unsigned)((B + 15) / 16), UP_NT, sizeof(EvalSmem<16>), (cudaStream_t)stream>>>(*p, critic_params, state, value, dV_ds, B);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_t, float beta1, float beta2, float eps,
+                               float* target_or_null, float tau, float* params_T_or_null, int32_t is_critic, int32_t ns, int32_t na,
+                               int64_t n, void* stream) {
+  if (!params || !grad || !m || !v) return CACTO_E_ARG;
+  int64_t total = 0;
+  LayerTable T = make_table(is_critic, ns, na, &total);
+  if (n != total) return CACTO_E_SIZE;
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, m, v, alpha_t, 1.f - beta1, 1.f - beta2, eps,
+                                                                       target_or_null, tau, params_T_or_null, T, n);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_transpose_params(const float* params, float* params_T, int32_t is_critic, int32_t ns, int32_t na, void* stream) {
+  if (!params || !params_T) return CACTO_E_ARG;
+  int64_t total = 0;
+  LayerTable T = make_table(is_critic, ns, na, &total);
+  k_transpose<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, params_T, T, total);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}

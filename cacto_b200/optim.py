@@ -1,0 +1,62 @@
+"""tf.keras.optimizers.Adam (TF 2.11) and PiecewiseConstantDecay on the fused CUDA Adam kernel.
+
+Reference use: RL.py:82-88 (construction, optional schedule), :105,:109 (apply_gradients).
+TF-2.11 update: t = iterations + 1; alpha_t = lr(iterations) sqrt(1 - b2^t) / (1 - b1^t);
+m += (g - m)(1 - b1); v += (g^2 - v)(1 - b2); p -= alpha_t m / (sqrt(v) + eps), eps = 1e-7 un-corrected.
+alpha_t is evaluated on the host in float32 like TF does on its float32 variables.
+"""
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .NeuralNetwork import Network
+
+
+class PiecewiseConstantDecay:
+    """values[#{boundaries < step}]  (tf.keras.optimizers.schedules.PiecewiseConstantDecay)."""
+
+    def __init__(self, boundaries, values):
+        assert len(values) == len(boundaries) + 1
+        self.boundaries, self.values = list(boundaries), list(values)
+
+    def __call__(self, step):
+        return self.values[sum(1 for b in self.boundaries if b < step)]
+
+
+class Adam:
+    def __init__(self, learning_rate, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+        self.iterations = 0
+        self._state = {}
+
+    def current_lr(self):
+        return self.learning_rate(self.iterations) if callable(self.learning_rate) else self.learning_rate
+
+    def _alpha(self):
+        f = np.float32
+        t = f(self.iterations + 1)
+        return float(f(self.current_lr()) * np.sqrt(f(1) - np.power(f(self.beta_2), t)) / (f(1) - np.power(f(self.beta_1), t)))
+
+    def step(self, net, target=None, tau=0.0):
+        """One Adam step on ``net`` from ``net.grad`` (zeroed afterwards); optionally the Polyak update
+        ``target = tau * net + (1 - tau) * target`` (RL.py:113-118) in the same launch."""
+        st = self._state.get(id(net))
+        if st is None:
+            st = (torch.zeros_like(net.params), torch.zeros_like(net.params))
+            self._state[id(net)] = st
+        m, v = st
+        check(lib.cacto_adam_step(ptr(net.params), ptr(net.grad), ptr(m), ptr(v), self._alpha(), self.beta_1, self.beta_2, self.epsilon,
+                                  ptr(target.params if target is not None else None), float(tau), ptr(net.params_T), net.is_critic,
+                                  net.ns, net.na, net.n, stream_ptr()), 'adam_step')
+        self.iterations += 1
+
+    def apply_gradients(self, grads_and_vars):
+        """Keras signature: ``apply_gradients(zip(grads, model.trainable_variables))``."""
+        grads, variables = zip(*list(grads_and_vars))
+        net = Network._registry.get(variables[0].data_ptr())
+        if net is None:
+            raise ValueError('variables do not belong to a cacto_b200 Network')
+        if grads[0].data_ptr() != net.grad.data_ptr():          # foreign gradients: stage them into the accumulator
+            for dst, g in zip(net._grad_views, grads):
+                dst.copy_(torch.as_tensor(g).to(dst.device, dst.dtype))
+        self.step(net)

@@ -138,10 +138,14 @@ int cacto_actor_grad(const cacto_sys_params* p, const float* actor_params, const
                      const double* term, float inv_B, float* grad, float* actions /* [B][na] or NULL */,
                      int64_t B, void* stream);
 
-/* ---- N8/N9: tf.keras Adam step (RL.py:105,109) with optional transposed-copy refresh and Polyak
- *      target update (RL.py:113-118).  alpha_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller. */
-int cacto_adam_step(float* params, const float* grad, float* m, float* v, float alpha_t, float beta1, float beta2,
-                    float eps, float* target_or_null, float tau, int64_t n, void* stream);
+/* ---- N8/N9: tf.keras Adam step (RL.py:105,109; TF 2.11: m += (g-m)(1-b1), v += (g^2-v)(1-b2),
+ *      p -= alpha_t m / (sqrt(v) + eps)) fused with the optional Polyak target update (RL.py:113-118:
+ *      target = tau p + (1-tau) target), the refresh of the transposed copy and the zeroing of `grad`.
+ *      alpha_t = lr(t-1) sqrt(1-b2^t)/(1-b1^t) is computed by the caller. n must equal the network's
+ *      parameter count. */
+int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_t, float beta1, float beta2,
+                    float eps, float* target_or_null, float tau, float* params_T_or_null, int32_t is_critic,
+                    int32_t ns, int32_t na, int64_t n, void* stream);
 
 /* Rebuild the per-layer transposed copy of a parameter block (W^T per layer, biases copied). */
 int cacto_transpose_params(const float* params, float* params_T, int32_t is_critic, int32_t ns, int32_t na,

@@ -111,7 +111,7 @@ def critic_grad(critic, target, conf, w_S, state, state_next, partial_rtg, dVdx,
     grads = torch.autograd.grad(loss, cp)
     with torch.no_grad():
         Vt = critic_forward(tp, t(state), conf)
-    return ([g.numpy() for g in grads], rtg.numpy(), V.detach().numpy(), Vt.numpy(), float(loss))
+    return ([g.numpy() for g in grads], rtg.numpy(), V.detach().numpy(), Vt.numpy(), float(loss.detach()))
 
 
 def actor_grad(actor, critic, conf, env, state, term, dtype=torch.float32):

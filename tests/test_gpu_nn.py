@@ -1,0 +1,151 @@
+"""CUDA actor/critic kernels (forward, Sobolev critic gradient, actor gradient, Adam, Polyak) against the
+oracle (torch-CPU autograd restatement of NeuralNetwork.py / RL.py).  BASELINE.md gate: losses and updated
+weights after one step within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from cacto_b200.conf import get_conf
+from conftest import golden
+from oracle import nn as onn
+from oracle import systems as osys
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def make(system, B, seed=0, w_S=1e-2, **over):
+    from cacto_b200 import environment as genv
+    from cacto_b200.NeuralNetwork import NN
+    from cacto_b200.RL import RL_AC
+    conf = get_conf(system, **over)
+    env = genv.make_env(conf)
+    nn = NN(env, conf, w_S, seed=seed)
+    rl = RL_AC(env, nn, conf, 0)
+    rl.setup_model()
+    rng = np.random.default_rng(seed + 1)
+    ns = conf.nb_state
+    lo, hi = np.asarray(conf.x_init_min, float), np.asarray(conf.x_init_max, float)
+    s = rng.uniform(lo, hi, (B, ns)).astype(np.float32)
+    sn = rng.uniform(lo, hi, (B, ns)).astype(np.float32)
+    if system == 'car_park':
+        for a in (s, sn):
+            a[:, 3] = rng.uniform(-3, 3, B)
+            a[:, 4] = rng.uniform(-0.5, 0.5, B)
+    pr = rng.uniform(-5, 0, (B, 1)).astype(np.float32)
+    dv = rng.normal(size=(B, ns)).astype(np.float32)
+    dv[:, -1] = 0
+    dv[0, 0] = 0.0                      # exercises the slog gradient gate at exactly 0 (quirk Q10)
+    d = (rng.uniform(size=(B, 1)) < 0.5).astype(np.float32)
+    term = (rng.uniform(size=(B, 1)) < 0.2).astype(np.float64)
+    w = rng.uniform(0.2, 1.5, (B, 1)).astype(np.float32)
+    return conf, env, nn, rl, (s, pr, sn, dv, d, term, w)
+
+
+SYSTEMS_B = [('single_integrator', 128), ('double_integrator', 37), ('car', 64), ('car_park', 64), ('manipulator', 64), ('ur5', 19),
+             ('manipulator', 2500)]
+
+
+@pytest.mark.parametrize('system,B', SYSTEMS_B)
+def test_forward_matches_oracle(system, B):
+    conf, env, nn, rl, batch = make(system, B)
+    s = batch[0]
+    ap, cp = onn.to_torch(rl.actor_model.get_weights()), onn.to_torch(rl.critic_model.get_weights())
+    st = torch.tensor(s, requires_grad=True)
+    a_ref = onn.actor_forward(ap, st, conf)
+    v_ref = onn.critic_forward(cp, st, conf)
+    g_ref, = torch.autograd.grad(v_ref.sum(), st)
+    assert rel(nn.eval(rl.actor_model, s), a_ref.detach().numpy()) < 2e-5
+    assert rel(nn.eval(rl.critic_model, s), v_ref.detach().numpy()) < 2e-5
+    V, dV = nn.eval_with_gradient(rl.critic_model, s)
+    assert rel(V, v_ref.detach().numpy()) < 2e-5
+    assert rel(dV, g_ref.numpy()) < 5e-5
+
+
+@pytest.mark.parametrize('system,B', SYSTEMS_B)
+@pytest.mark.parametrize('w_S', [1e-2, 0.0])
+def test_critic_and_actor_gradients_match_oracle(system, B, w_S):
+    conf, env, nn, rl, batch = make(system, B, w_S=w_S)
+    s, pr, sn, dv, d, term, w = batch
+    critic, target, actor = rl.critic_model.get_weights(), rl.target_critic.get_weights(), rl.actor_model.get_weights()
+    target = [t + 0.01 * np.random.default_rng(5).normal(size=t.shape).astype(np.float32) for t in target]
+    rl.target_critic.set_weights(target)
+    cg, rtg, V, Vt, loss = onn.critic_grad(critic, target, conf, w_S, s, sn, pr, dv, d, w)
+    g, g_rtg, g_V, g_Vt = nn.compute_critic_grad(rl.critic_model, rl.target_critic, s, sn, pr, dv, d, w)
+    assert rel(g_rtg, rtg) < 2e-5 and rel(g_V, V) < 2e-5 and rel(g_Vt, Vt) < 2e-5
+    assert abs(float(nn.last_critic_loss) - loss) <= 1e-4 * abs(loss)
+    for gv, rv in zip(g, cg):
+        assert rel(gv, rv) < 1e-4
+    oenv = osys.make_env(conf)
+    ag, actions, s_next, dQ = onn.actor_grad(actor, critic, conf, oenv, s, term)
+    ga, act = nn.compute_actor_grad(rl.actor_model, rl.critic_model, s, term, None, return_actions=True)
+    assert rel(act, actions) < 2e-5
+    for gv, rv in zip(ga, ag):
+        assert rel(gv, rv) < 1e-4
+
+
+@pytest.mark.parametrize('system,B', [('manipulator', 64), ('double_integrator', 128), ('ur5', 16), ('car', 2400)])
+def test_one_update_step_matches_oracle(system, B):
+    """RL_AC.update + update_target: weights of critic, actor and target after one (and two) steps."""
+    conf, env, nn, rl, batch = make(system, B)
+    s, pr, sn, dv, d, term, w = batch
+    critic, target, actor = rl.critic_model.get_weights(), rl.target_critic.get_weights(), rl.actor_model.get_weights()
+    before = [x.copy() for x in critic + actor]
+    oc, oa = onn.Adam(critic, conf.CRITIC_LEARNING_RATE), onn.Adam(actor, conf.ACTOR_LEARNING_RATE)
+    oenv = osys.make_env(conf)
+    for step in range(2):
+        out = onn.update(critic, target, actor, oc, oa, conf, 1e-2, oenv, (s, pr, sn, dv, d, term, w))
+        rtg, V, Vt = rl.update(s, sn, pr, dv, d, term, w)
+        rl.update_target(rl.target_critic.variables, rl.critic_model.variables)
+        assert rel(rtg, out['rtg']) < 2e-5 and rel(V, out['V']) < 2e-5
+        mine = rl.critic_model.get_weights() + rl.actor_model.get_weights()
+        for k, (m, r, b0) in enumerate(zip(mine, critic + actor, before)):
+            assert rel(m, r) < 1e-4, (step, k)
+            # the step itself (|dw| ~ lr): compare against the oracle's step with a tolerance relative to lr
+            lr = conf.CRITIC_LEARNING_RATE if k < 10 else conf.ACTOR_LEARNING_RATE
+            assert np.abs((m - b0) - (r - b0)).max() < 0.02 * lr * (step + 1), (step, k)
+        for m, r in zip(rl.target_critic.get_weights(), target):
+            assert rel(m, r) < 1e-5
+
+
+def test_fused_target_update_equals_separate():
+    conf, env, nn, rl, batch = make('manipulator', 64)
+    s, pr, sn, dv, d, term, w = batch
+    w0 = [rl.critic_model.get_weights(), rl.target_critic.get_weights(), rl.actor_model.get_weights()]
+    rl.update(s, sn, pr, dv, d, term, w, fuse_target=True)
+    fused = rl.target_critic.get_weights()
+    conf2, env2, nn2, rl2, _ = make('manipulator', 64)
+    rl2.critic_model.set_weights(w0[0]); rl2.target_critic.set_weights(w0[1]); rl2.actor_model.set_weights(w0[2])
+    rl2.update(s, sn, pr, dv, d, term, w)
+    rl2.update_target(rl2.target_critic.variables, rl2.critic_model.variables)
+    for a, b in zip(fused, rl2.target_critic.get_weights()):
+        assert rel(a, b) < 1e-6
+
+
+def test_lr_schedule_and_adam_iterations():
+    from cacto_b200.optim import PiecewiseConstantDecay
+    conf = get_conf('manipulator')
+    sch = PiecewiseConstantDecay(conf.boundaries_schedule_LR_C, conf.values_schedule_LR_C)
+    for step in (0, 1, 204800, 204801, 307200, 307201, 600000):
+        assert sch(step) == onn.piecewise_lr(step, conf.boundaries_schedule_LR_C, conf.values_schedule_LR_C)
+    assert sch(204800) == conf.values_schedule_LR_C[0] and sch(204801) == conf.values_schedule_LR_C[1]
+
+
+def test_reference_h5_weights_forward():
+    """BASELINE config 1: the reference's archived Keras weights (Results Single Integrator/.../N_try_0/*_0.h5)."""
+    g = golden('h5_si_try0.npz')
+    conf, env, nn, rl, batch = make('single_integrator', 128)
+    rl.actor_model.set_weights([g[f'actor_{i}'] for i in range(6)])
+    rl.critic_model.set_weights([g[f'critic_{i}'] for i in range(10)])
+    s = batch[0]
+    st = torch.tensor(s)
+    a_ref = onn.actor_forward(onn.to_torch([g[f'actor_{i}'] for i in range(6)]), st, conf).numpy()
+    v_ref = onn.critic_forward(onn.to_torch([g[f'critic_{i}'] for i in range(10)]), st, conf).numpy()
+    assert rel(nn.eval(rl.actor_model, s), a_ref) < 2e-5
+    assert rel(nn.eval(rl.critic_model, s), v_ref) < 2e-5

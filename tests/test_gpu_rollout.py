@@ -1,0 +1,106 @@
+"""Fused actor + dynamics rollout kernel (K1) against the oracle's restatement of RL_AC.create_TO_init and the
+reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+
+from cacto_b200.conf import SYSTEM_IDS, get_conf
+from conftest import golden
+from oracle import nn as onn
+from oracle import rtg as ortg
+from oracle import systems as osys
+
+pytestmark = pytest.mark.gpu
+
+
+def setup(system, seed=0):
+    from cacto_b200 import environment as genv
+    from cacto_b200.NeuralNetwork import NN
+    from cacto_b200.RL import RL_AC
+    conf = get_conf(system)
+    env = genv.make_env(conf)
+    rl = RL_AC(env, NN(env, conf, 1e-2, seed=seed), conf, 0)
+    rl.setup_model()
+    return conf, env, rl
+
+
+def ics(conf, B, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(np.asarray(conf.x_init_min, float), np.asarray(conf.x_init_max, float), (B, conf.nb_state))
+    x[:, -1] = conf.dt * np.round(x[:, -1] / conf.dt)
+    return x
+
+
+@pytest.mark.parametrize('system', SYSTEM_IDS)
+@pytest.mark.parametrize('ep', [0, 1])
+def test_rollout_batch_matches_oracle(system, ep):
+    conf, env, rl = setup(system)
+    B = 70 if system != 'ur5' else 5          # 70: two CTAs, ragged tile, mixed horizons
+    X0 = ics(conf, B, 3)
+    X0[0, -1] = 0.0                            # full horizon
+    X0[1, -1] = (conf.NSTEPS - 1) * conf.dt    # one step
+    out = rl.rollout_batch(X0, ep)
+    states = out['states'].permute(2, 0, 1).cpu().numpy()
+    controls = out['controls'].permute(2, 0, 1).cpu().numpy()
+    hz = out['horizon'].cpu().numpy()
+    assert out['success'].cpu().numpy().all()
+    oenv = osys.make_env(conf)
+    ap = onn.to_torch(rl.actor_model.get_weights())
+
+    def actor_eval(x):
+        with torch.no_grad():
+            return onn.actor_forward(ap, torch.tensor(x, dtype=torch.float32), conf).numpy()[0]
+    n_check = B if system != 'ur5' else 3
+    for b in range(n_check):
+        _, st, ct, T, ok = ortg.create_to_init(conf, oenv, actor_eval, ep, X0[b])
+        assert ok == 1 and T == hz[b] == ortg.horizon(conf, X0[b, -1])
+        sc = np.abs(st).max(axis=0) + 1e-12
+        assert (np.abs(states[b, :T + 1] - st) / sc).max() < 1e-4, (b, T)
+        if T > 0:
+            assert np.abs(controls[b, :T] - ct).max() <= 1e-4 * max(np.abs(ct).max(), 1e-3)
+        assert np.isnan(states[b, T + 1:]).all()          # entries past the horizon are untouched
+
+
+@pytest.mark.parametrize('system', ['single_integrator', 'car', 'car_park'])
+def test_create_TO_init_matches_reference_goldens(system):
+    """The reference's own create_TO_init loop (tests/golden/toinit_cases.npz)."""
+    g = golden('toinit_cases.npz')
+    conf, env, rl = setup(system)
+    rl.actor_model.set_weights([g[f'{system}_actor_{i}'] for i in range(6)])
+    for k in range(3):
+        for ep in (0, 1):
+            x0 = g[f'{system}_{k}_{ep}_ics']
+            _, st, ct, T, ok = rl.create_TO_init(ep, x0)
+            assert ok == 1 and T == int(g[f'{system}_{k}_{ep}_T'])
+            ref_s, ref_c = g[f'{system}_{k}_{ep}_states'], g[f'{system}_{k}_{ep}_controls']
+            tol = 1e-12 if ep == 0 else 1e-4
+            sc = np.abs(ref_s).max(axis=0) + 1e-12
+            assert (np.abs(st - ref_s) / sc).max() <= tol
+            assert np.abs(ct - ref_c).max() <= tol * max(1.0, np.abs(ref_c).max())
+
+
+def test_horizon_zero_and_nan_flag():
+    conf, env, rl = setup('manipulator')
+    x0 = ics(conf, 4, 1)
+    x0[0, -1] = conf.NSTEPS * conf.dt          # NSTEPS_SH = 0 (RL.py:202-203)
+    assert rl.create_TO_init(1, x0[0])[-1] == 0
+    x0[1, 0] = np.nan
+    out = rl.rollout_batch(x0, 1)
+    ok = out['success'].cpu().numpy()
+    assert ok[1] == 0 and ok[2] == 1 and ok[3] == 1
+
+
+def test_rollout_rewards_match_env_step():
+    """PLOT.rollout-style rewards (plot_utils.py:261-268): running reward at (x_t, u_t), terminal at x_T."""
+    conf, env, rl = setup('manipulator')
+    x0 = ics(conf, 6, 2)
+    out = rl.rollout_batch(x0, 1, with_reward=True)
+    oenv = osys.make_env(conf)
+    S = out['states'].permute(2, 0, 1).cpu().numpy()
+    U = out['controls'].permute(2, 0, 1).cpu().numpy()
+    R = out['rewards'].permute(1, 0).cpu().numpy()
+    hz = out['horizon'].cpu().numpy()
+    for b in range(6):
+        T = hz[b]
+        ref = [oenv.reward(conf.cost_weights_running, S[b, t], U[b, t]) for t in range(T)] + [oenv.reward(conf.cost_weights_terminal, S[b, T])]
+        np.testing.assert_allclose(R[b, :T + 1], ref, rtol=1e-9, atol=1e-14)
