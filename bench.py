@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- CACTO hot-path throughput on B200 (BASELINE.json metric: manipulator rollout env-steps/s
++ Sobolev actor-critic updates/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the fused rollout kernel (K1) over this rank's batch of synthetic initial
+conditions: BASELINE config[3] (3-DOF planar manipulator, 1 M rollouts x 100 steps sharded over 8 GPUs)
+= 131072 rollouts x 100 env-steps per GPU (weak scaling: per-GPU work fixed).  `value` counts env-steps
+with the inputs resident in HBM; `e2e` runs the same pass through the public Python API with the initial
+conditions in pinned HOST memory and the warm-start trajectories copied back to pinned host memory inside
+the timed region.  The secondary number (Sobolev critic+actor updates/s, conf batch 64 per GPU) is in
+`extra`.  `cpu_baseline` times the oracle's restatement of the reference's rollout loop
+(RL.py:221-231 over multiprocessing.Pool like main.py:220-225) on the host cores, on a bounded sample.
+`--impl reference` prints that CPU arm alone as the reference line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SYSTEM = 'manipulator'
+ROLLOUTS_PER_GPU = 131072
+P_ACTOR_MACS = 256 * 7 + 65536 + 256 * 3          # P_a for the manipulator
+F_DYN = 250                                        # flops of the planar-3R forward dynamics step
+FLOPS_PER_ENV_STEP = 2 * P_ACTOR_MACS + F_DYN
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """One worker of the reference-structured CPU rollout: B=1 actor forward + one simulate per step."""
+    import torch
+    torch.set_num_threads(1)
+    from cacto_b200.conf import get_conf
+    from oracle import nn as onn, rtg as ortg, systems as osys
+    seed, n_rollouts, weights = args
+    conf = get_conf(SYSTEM)
+    env = osys.make_env(conf)
+    ap = onn.to_torch(weights)
+    rng = np.random.default_rng(seed)
+
+    def actor_eval(x):
+        with torch.no_grad():
+            return onn.actor_forward(ap, torch.tensor(x, dtype=torch.float32), conf).numpy()[0]
+    steps = 0
+    for _ in range(n_rollouts):
+        x0 = rng.uniform(conf.x_init_min, conf.x_init_max)
+        x0[-1] = 0.0
+        _, st, ct, T, ok = ortg.create_to_init(conf, env, actor_eval, 1, x0)
+        steps += T
+    return steps
+
+
+def cpu_rollout_rate(cores, rollouts_per_core):
+    """env-steps/s of the CPU arm on `cores` processes (fork; must run before CUDA is initialised)."""
+    import multiprocessing as mp
+    from oracle import nn as onn
+    weights = onn.init_actor(7, 3, seed=0)
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(100 + i, 1, weights) for i in range(cores)])          # warm-up: imports, page-in
+        t0 = time.perf_counter()
+        steps = sum(pool.map(_cpu_worker, [(i, rollouts_per_core, weights) for i in range(cores)]))
+        dt = time.perf_counter() - t0
+    return steps / dt, steps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    per_core = 6
+    for _ in range(args.warmup):
+        cpu_rollout_rate(cores, 1)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        rate, steps, dt = cpu_rollout_rate(cores, per_core)
+        vals.append((rate, steps, dt))
+    total_steps = sum(v[1] for v in vals)
+    total_dt = sum(v[2] for v in vals)
+    rate = total_steps / total_dt
+    sample = f'{cores * per_core} rollouts x 100 steps per bench step ({total_steps} env-steps in {total_dt:.1f} s), t0 = 0'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'manipulator rollout env-steps/s', 'value': rate, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_dt / max(1, args.steps), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 actor / f64 dynamics', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE config[3]: manipulator policy rollouts (RL.py:221-231 structure), CPU', 'sample': sample},
+        'cpu_baseline': {'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i',
+                                          str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    K, W = args.steps, args.warmup
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:          # before CUDA init: the pool forks
+        cores = os.cpu_count() or 1
+        per_core = 12
+        rate, steps, dt = cpu_rollout_rate(cores, per_core)
+        cpu = {'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+               'sample': f'{cores * per_core} rollouts x 100 steps ({steps} env-steps, {dt:.1f} s): oracle restatement of RL.py:221-231 '
+                         f'(B=1 torch-CPU actor forward + NumPy fp64 dynamics per step) over multiprocessing.Pool({cores})'}
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback on the product path)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from cacto_b200 import _lib, environment as genv
+    from cacto_b200.NeuralNetwork import NN
+    from cacto_b200.RL import RL_AC
+    from cacto_b200.conf import get_conf
+
+    conf = get_conf(SYSTEM)
+    env = genv.make_env(conf)
+    rl = RL_AC(env, NN(env, conf, 1e-2, seed=0), conf, 0, dist=dist if world > 1 else None)
+    rl.setup_model()
+    B, T, ns, na = args.rollouts_per_gpu, conf.NSTEPS, conf.nb_state, conf.nb_action
+    rng = np.random.default_rng(1000 + rank)
+    X0 = rng.uniform(conf.x_init_min, conf.x_init_max, (B, ns))
+    X0[:, -1] = 0.0                                            # full horizon: fixed work B x NSTEPS env-steps per step
+    ics_host = torch.as_tensor(X0).pin_memory()
+    ics = ics_host.to(dev)
+    hz = torch.full((B,), T, dtype=torch.int32, device=dev)
+    states = torch.empty((T + 1, ns, B), dtype=torch.float64, device=dev)
+    controls = torch.empty((T, na, B), dtype=torch.float64, device=dev)
+    flags = torch.empty(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MiB > 126 MB L2
+    stream = torch.cuda.current_stream()
+    P = env._p
+    lib, ptr, check = _lib.lib, _lib.ptr, _lib.check
+
+    def rollout_step():
+        check(lib.cacto_rollout(P, ptr(rl.actor_model.params), 1, ptr(ics), ptr(hz), T, ptr(states), ptr(controls), ptr(flags), ptr(None),
+                                B, _lib.stream_ptr()), 'rollout')
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, do_flush=True):
+        """Sum of per-step CUDA-event durations (ms) on the launching stream; L2 flushed between steps."""
+        evs = []
+        for _ in range(steps):
+            if do_flush:
+                flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    # FP32 FMA peak, measured in-run (roofline denominator of the fp32-FMA rollout kernel)
+    pk_out = torch.zeros(4, dtype=torch.float32, device=dev)
+    pk_iters, pk_blocks = 4096, 148 * 16
+    for _ in range(2):
+        lib.cacto_peak_fma_fp32(ptr(pk_out), pk_iters, pk_blocks, _lib.stream_ptr())
+    pk_ms = min(timed(lambda: lib.cacto_peak_fma_fp32(ptr(pk_out), pk_iters, pk_blocks, _lib.stream_ptr()), 5, do_flush=False))
+    fma_peak_tflops = pk_blocks * 256 * pk_iters * 16 * 2 / (pk_ms * 1e-3) / 1e12
+
+    # ---- K1 rollouts: device-resident
+    for _ in range(W):
+        rollout_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(rollout_step, K)
+    barrier()
+    total_ms = float(sum(ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0])
+    assert bool(flags.all()), 'a rollout hit NaN'
+    env_steps = B * T * K * world
+    value = env_steps / (total_ms * 1e-3)
+    kernel_ms = float(np.mean(ms))
+    achieved_tflops = B * T * FLOPS_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e12
+
+    # ---- e2e: host ICS (pinned) -> H2D -> rollout -> D2H of the warm-start trajectories (pinned)
+    st_host = torch.empty((T + 1, ns, B), dtype=torch.float64).pin_memory()
+    ct_host = torch.empty((T, na, B), dtype=torch.float64).pin_memory()
+    fl_host = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        out = rl.rollout_to_host(ics_host, 1, st_host, ct_host, fl_host)
+        return out
+    for _ in range(max(1, W // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = B * T * K * world / e2e_s
+    h2d = ics_host.numel() * 8
+    d2h = (st_host.numel() + ct_host.numel()) * 8 + fl_host.numel() * 4
+
+    # ---- K3 updates/s (secondary metric): conf batch per GPU, data resident, gradients all-reduced over NCCL
+    Bu = conf.BATCH_SIZE
+    g = torch.Generator(device='cpu').manual_seed(rank)
+    lo, hi = torch.as_tensor(conf.x_init_min), torch.as_tensor(conf.x_init_max)
+    s = (lo + (hi - lo) * torch.rand((Bu, ns), generator=g, dtype=torch.float64)).float().to(dev)
+    sn = (lo + (hi - lo) * torch.rand((Bu, ns), generator=g, dtype=torch.float64)).float().to(dev)
+    pr = (-5 * torch.rand((Bu, 1), generator=g)).to(dev)
+    dv = torch.randn((Bu, ns), generator=g).to(dev); dv[:, -1] = 0
+    d = (torch.rand((Bu, 1), generator=g) < 0.5).float().to(dev)
+    term = (torch.rand((Bu, 1), generator=g) < 0.01).double().to(dev)
+    w = torch.ones((Bu, 1), device=dev)
+
+    def update_step():
+        rl.update(s, sn, pr, dv, d, term, w, fuse_target=True)
+    n_up = 200
+    for _ in range(20):
+        update_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(n_up):
+        update_step()
+    b.record(stream)
+    torch.cuda.synchronize()
+    up_ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([up_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        up_ms = float(t[0])
+    updates_per_s = n_up / (up_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        line = {
+            'metric': 'manipulator rollout env-steps/s', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 actor MLP / f64 dynamics', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE config[3]: 3-DOF planar manipulator policy rollouts (create_TO_init), '
+                                   f'{B} rollouts x {T} steps per GPU (1 M over 8 GPUs), seeded-init actor {ns}->256->256->{na}',
+                       'rollouts_per_gpu': B, 'horizon': T, 'l2': 'flushed between timed steps (256 MiB write); outputs 1.06 GB/step',
+                       'parallelism': f'dp{world} over independent rollouts, no collective on the rollout path'},
+            'roofline': {'bound': 'fp32_fma', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
+                         'frac': achieved_tflops / fma_peak_tflops, 'traffic': None,
+                         'note': 'k_rollout is an fp32 CUDA-core FMA contraction (parity gate 1e-5 rules out bf16/tf32 UMMA); peak = FP32 FMA '
+                                 'rate measured in this run (cacto_peak_fma_fp32). Against the measured bf16 tensor peak '
+                                 f"({peaks.get('bf16_tflops')} TFLOP/s) the fraction is {achieved_tflops / peaks['bf16_tflops'] if peaks.get('bf16_tflops') else None}",
+                         'flops_per_env_step': FLOPS_PER_ENV_STEP, 'kernel_ms': kernel_ms},
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': K,
+            'clocks': clocks,
+            'extra': {'sobolev_updates_per_s': updates_per_s, 'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world,
+                      'update_launches_per_update': 4, 'fp32_fma_peak_tflops_measured': fma_peak_tflops},
+        }
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--rollouts-per-gpu', type=int, default=ROLLOUTS_PER_GPU)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

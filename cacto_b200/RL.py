@@ -182,6 +182,40 @@ class RL_AC:
             out['rewards'] = rewards
         return out
 
+    def rollout_to_host(self, ics_host, ep, states_host, controls_host, flags_host, mode='staged'):
+        """Host-to-host rollouts for the TO feeder: ``ics_host`` [B, ns] fp64 (pinned) -> ``states_host``
+        [T_max+1, ns, B], ``controls_host`` [T_max, na, B] fp64 and ``flags_host`` [B] int32 (pinned).
+        mode 'staged': H2D, kernel into HBM, D2H.  mode 'zero_copy': the kernel stores the trajectories
+        straight into the pinned host buffers over PCIe (UVA), overlapping the transfer with the compute."""
+        c = self.conf
+        dev = _device()
+        B = ics_host.shape[0]
+        T_max = int(c.NSTEPS)
+        ics = ics_host.to(dev, non_blocking=True)
+        hz_np = self.horizon(ics_host.numpy())
+        hz = torch.as_tensor(hz_np).to(dev, non_blocking=True)
+        use_actor = int(ep != 0)
+        actor = self.actor_model.params if use_actor else None
+        if mode == 'zero_copy':
+            flags = torch.empty(B, dtype=torch.int32, device=dev)
+            check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(states_host), ptr(controls_host),
+                                    ptr(flags), ptr(None), B, stream_ptr()), 'rollout')
+            flags_host.copy_(flags, non_blocking=True)
+        else:
+            buf = getattr(self, '_host_stage', None)
+            if buf is None or buf[0].shape[2] != B:
+                buf = (torch.empty((T_max + 1, c.nb_state, B), dtype=torch.float64, device=dev),
+                       torch.empty((T_max, c.nb_action, B), dtype=torch.float64, device=dev),
+                       torch.empty(B, dtype=torch.int32, device=dev))
+                self._host_stage = buf
+            check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(buf[0]), ptr(buf[1]), ptr(buf[2]),
+                                    ptr(None), B, stream_ptr()), 'rollout')
+            states_host.copy_(buf[0], non_blocking=True)
+            controls_host.copy_(buf[1], non_blocking=True)
+            flags_host.copy_(buf[2], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return hz_np
+
     def create_TO_init(self, ep, ICS):
         """RL.py:197-233 for one initial condition -> (ICS, init_TO_states[T+1, ns], init_TO_controls[T, na], T, success)."""
         self.init_rand_state = ICS

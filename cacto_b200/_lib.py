@@ -99,7 +99,8 @@ _SIGNATURES = {
     'cacto_critic_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 6 +
     [C.c_float] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]),
     'cacto_actor_grad': (C.c_int, [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    'cacto_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_float] * 4 + [C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+    'cacto_adam_schedule': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'cacto_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p] + [C.c_float] * 3 + [C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int64, C.c_void_p]),
     'cacto_transpose_params': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'cacto_segtree_update': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -108,6 +109,7 @@ _SIGNATURES = {
                                        C.c_void_p, C.c_void_p]),
     'cacto_segtree_find': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'cacto_buffer_gather': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p]),
+    'cacto_peak_fma_fp32': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'cacto_rtg_window': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] +
                          [C.c_void_p] * 6 + [C.c_void_p]),
 }

@@ -90,6 +90,119 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
   }
 }
 
+// ------------------------------------------------------------------------------------------ weight pipeline
+// Weights streamed into shared memory by the TMA engine: one elected thread issues a 1-D bulk copy
+// (cp.async.bulk, SASS UBLKCP) of a contiguous chunk of <= W_CHUNK floats from global/L2 into one of two
+// shared slots and an mbarrier counts the landed bytes; all threads then read the chunk with conflict-free
+// LDS.128.  While a chunk is consumed the next one (of the same GEMM or the first chunk of the next GEMM)
+// is already in flight, so the L2 latency of a weight fetch is paid once per kernel, not once per k-step
+// (the latter made the B = 64 update latency-bound: profiles/r1_update_latency.md).
+constexpr int W_CHUNK = 8192;   // floats per slot (32 KB)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct WeightPipe {
+  float* buf;          // 2 * W_CHUNK floats, 128-byte aligned
+  uint64_t* bar;       // 2 mbarriers
+  unsigned issued, consumed;
+
+  __device__ __forceinline__ void init(float* b, uint64_t* br) {
+    buf = b; bar = br; issued = 0; consumed = 0;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // All threads call; thread 0 issues.  The target slot must no longer be read by any thread
+  // (callers guarantee it with the __syncthreads() that ends the consumption of a chunk).
+  __device__ __forceinline__ void issue(const float* __restrict__ g, int nfloats) {
+    if (threadIdx.x == 0 && g != nullptr) {
+      const unsigned slot = issued & 1u;
+      const uint32_t bytes = (uint32_t)nfloats * 4u;
+      const uint32_t mb = smem_u32(&bar[slot]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(buf + slot * W_CHUNK)),
+                   "l"(g), "r"(bytes), "r"(mb)
+                   : "memory");
+    }
+    if (g != nullptr) ++issued;
+  }
+  __device__ __forceinline__ const float* wait() {
+    const unsigned slot = consumed & 1u, parity = (consumed >> 1) & 1u;
+    const uint32_t mb = smem_u32(&bar[slot]);
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (!done) {
+      if (++spins > (1u << 24)) __trap();      // a chunk that was never issued: fail loudly instead of hanging the GPU
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(mb), "r"(parity)
+          : "memory");
+    }
+    ++consumed;
+    return buf + slot * W_CHUNK;
+  }
+};
+
+template <int N>
+__host__ __device__ constexpr int chunk_rows(int K) { return (W_CHUNK / N) < K ? (W_CHUNK / N) : K; }
+
+// C = A * W with W [K x N] (row-major, ld = N, K % 4 == 0) streamed through the weight pipeline.
+// Contract: the first chunk of W is already in flight; while the last chunk is being consumed the first
+// chunk of `next` (next_floats floats, nullptr for none) is issued.  Ends WITHOUT a trailing barrier for
+// the epilogue: the caller places the __syncthreads() that publishes C (as with tile_gemm).
+template <int S, int N, int NT, typename Epi>
+__device__ __forceinline__ void gemm_streamed(WeightPipe& pipe, const float* __restrict__ A, int lda, int K,
+                                              const float* __restrict__ Wg, const float* __restrict__ next, int next_floats, Epi&& epi) {
+  typedef GemmMap<S, N, NT> M;
+  constexpr int TM = M::TM;
+  const int cg = threadIdx.x % M::CG, rg = threadIdx.x / M::CG;
+  const bool active = rg < M::RG;
+  float4 acc[TM];
+#pragma unroll
+  for (int r = 0; r < TM; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int rows_per_chunk = chunk_rows<N>(K);
+  const int nchunks = (K + rows_per_chunk - 1) / rows_per_chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int k0 = c * rows_per_chunk;
+    const int kc = min(rows_per_chunk, K - k0);
+    if (c + 1 < nchunks) {
+      const int kn = min(rows_per_chunk, K - (k0 + rows_per_chunk));
+      pipe.issue(Wg + (size_t)(k0 + rows_per_chunk) * N, kn * N);
+    } else {
+      pipe.issue(next, next_floats);
+    }
+    const float* w = pipe.wait();
+    if (active) {
+      const float* a0 = A + (size_t)(rg * TM) * lda + k0;
+      const float4* wp = reinterpret_cast<const float4*>(w) + cg;
+#pragma unroll 2
+      for (int k = 0; k < kc; k += 4) {
+        const float4 w0 = wp[(k + 0) * (N / 4)], w1 = wp[(k + 1) * (N / 4)], w2 = wp[(k + 2) * (N / 4)], w3 = wp[(k + 3) * (N / 4)];
+#pragma unroll
+        for (int r = 0; r < TM; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(a0 + r * lda + k);
+          fma4(acc[r], a.x, w0);
+          fma4(acc[r], a.y, w1);
+          fma4(acc[r], a.z, w2);
+          fma4(acc[r], a.w, w3);
+        }
+      }
+    }
+    __syncthreads();          // every thread is done with this slot before it is refilled
+  }
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < TM; ++r) epi(rg * TM + r, 4 * cg, acc[r]);
+  }
+}
+
 // C[s][j] = sum_k A[s][k] * w(k, j) for tiny N.  W_KN: w(k, j) = W[k*N + j]; otherwise w(k, j) = W[j*ldw + k]
 // (rows of a [N x K] matrix).  G lanes cooperate on one output.  epi(row, j, value).
 template <int S, int NT, int G, bool W_KN, typename Epi>

@@ -15,6 +15,7 @@ namespace cacto {
 
 constexpr int RO_S = 64;      // rollouts per CTA
 constexpr int RO_NT = 256;    // threads per CTA
+constexpr int RO_MIN_CTAS = 2; // resident CTAs per SM the register budget is capped for (<= 128 registers)
 constexpr int NSP = 16;       // padded input width (>= CACTO_MAX_NS, multiple of 4)
 constexpr int NAP = 8;        // padded action width
 
@@ -26,7 +27,7 @@ struct RolloutSmem {
 };
 
 template <int SYS>
-__global__ void __launch_bounds__(RO_NT) k_rollout(const __grid_constant__ cacto_sys_params P, const float* __restrict__ actor,
+__global__ void __launch_bounds__(RO_NT, RO_MIN_CTAS) k_rollout(const __grid_constant__ cacto_sys_params P, const float* __restrict__ actor,
                                                    int use_actor, const double* __restrict__ ics, const int32_t* __restrict__ horizon,
                                                    int T_max, double* __restrict__ states, double* __restrict__ controls,
                                                    int32_t* __restrict__ flags, double* __restrict__ rewards, int64_t B) {
@@ -113,6 +114,8 @@ static int launch_rollout(const cacto_sys_params& P, const float* actor, int use
   auto k = k_rollout<SYS>;
   const size_t sm = sizeof(RolloutSmem);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return (int)e;
   k<<<(unsigned)((B + RO_S - 1) / RO_S), RO_NT, sm, st>>>(P, actor, use_actor, ics, horizon, T_max, states, controls, flags, rewards, B);
   CACTO_LAUNCH_CHECK();

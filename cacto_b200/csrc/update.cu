@@ -29,6 +29,20 @@ __host__ __device__ __forceinline__ constexpr int koff(int l) { return l == 0 ? 
 __device__ __forceinline__ float slog(float x) { return x > 0.f ? logf(fmaxf(x, 1e-7f) + 1.f) : -logf(fmaxf(-x, 1e-7f) + 1.f); }
 __device__ __forceinline__ float slog_grad(float x) { return fabsf(x) >= 1e-7f ? 1.f / (fabsf(x) + 1.f) : 0.f; }
 
+// Order in which the streamed (K % 4 == 0) weight matrices are consumed by a kernel; built by every
+// thread identically, read when a GEMM asks the pipeline to prefetch its successor.
+struct WeightSeq {
+  const float* ptr[24];
+  int first[24];      // floats of the first chunk
+  int n;
+};
+template <int N>
+__device__ __forceinline__ void seq_push(WeightSeq& q, const float* p, int K) {
+  q.ptr[q.n] = p;
+  q.first[q.n] = chunk_rows<N>(K) * N;
+  ++q.n;
+}
+
 // Load `rows` rows of a [B][ns] float state block, normalise (utils.py:17-24) and zero-pad to [S][NSP].
 template <int S>
 __device__ __forceinline__ void load_normalised(const cacto_sys_params& P, const float* __restrict__ g, int64_t row0, int rows,
@@ -42,27 +56,46 @@ __device__ __forceinline__ void load_normalised(const cacto_sys_params& P, const
   }
 }
 
+// Streamed GEMM number `gi` of the kernel's weight sequence (prefetches the first chunk of number gi + 1).
+template <int S, int N, typename SM, typename Epi>
+__device__ __forceinline__ void streamed(WeightPipe& pipe, SM& sm, int& gi, const float* A, int lda, int K, Epi&& epi) {
+  const bool more = gi + 1 < sm.seq.n;
+  gemm_streamed<S, N, UP_NT>(pipe, A, lda, K, sm.seq.ptr[gi], more ? sm.seq.ptr[gi + 1] : nullptr, more ? sm.seq.first[gi + 1] : 0, epi);
+  ++gi;
+}
+// the three streamed layers of a critic forward (weights w) / of a sweep with the transposed weights (wT)
+__device__ __forceinline__ void seq_push_critic_fwd(WeightSeq& q, const CriticLayout& L, const float* w) {
+  seq_push<CR_H2>(q, w + L.W[1], CR_H1);
+  seq_push<CR_H3>(q, w + L.W[2], CR_H2);
+  seq_push<CR_H4>(q, w + L.W[3], CR_H3);
+}
+__device__ __forceinline__ void seq_push_critic_bwd(WeightSeq& q, const CriticLayout& L, const float* wT) {
+  seq_push<CR_H3>(q, wT + L.W[3], CR_H4);
+  seq_push<CR_H2>(q, wT + L.W[2], CR_H3);
+  seq_push<CR_H1>(q, wT + L.W[1], CR_H2);
+}
+
 // Forward pass of the sine critic for a tile, activations ping-ponging between two [S][ld] scratch
 // buffers (>= 128 columns used).  V[s] receives the value.  Ends with a __syncthreads().
-template <int S>
-__device__ __forceinline__ void critic_forward_tile(const float* __restrict__ cw, const CriticLayout& L, const float (*XN)[NSP],
-                                                    float* bufA, float* bufB, int ld, float* V) {
+template <int S, typename SM>
+__device__ __forceinline__ void critic_forward_tile(WeightPipe& pipe, SM& sm, int& gi, const float* __restrict__ cw, const CriticLayout& L,
+                                                    const float (*XN)[NSP], float* bufA, float* bufB, int ld, float* V) {
   tile_gemm<S, CR_H1, UP_NT, false>(&XN[0][0], NSP, L.ns, cw + L.W[0], CR_H1, [&](int r, int c, const float4& a) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[0] + c));
     *reinterpret_cast<float4*>(bufA + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
   });
   __syncthreads();
-  tile_gemm<S, CR_H2, UP_NT, false>(bufA, ld, CR_H1, cw + L.W[1], CR_H2, [&](int r, int c, const float4& a) {
+  streamed<S, CR_H2>(pipe, sm, gi, bufA, ld, CR_H1, [&](int r, int c, const float4& a) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[1] + c));
     *reinterpret_cast<float4*>(bufB + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
   });
   __syncthreads();
-  tile_gemm<S, CR_H3, UP_NT, false>(bufB, ld, CR_H2, cw + L.W[2], CR_H3, [&](int r, int c, const float4& a) {
+  streamed<S, CR_H3>(pipe, sm, gi, bufB, ld, CR_H2, [&](int r, int c, const float4& a) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[2] + c));
     *reinterpret_cast<float4*>(bufA + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
   });
   __syncthreads();
-  tile_gemm<S, CR_H4, UP_NT, false>(bufA, ld, CR_H3, cw + L.W[3], CR_H4, [&](int r, int c, const float4& a) {
+  streamed<S, CR_H4>(pipe, sm, gi, bufA, ld, CR_H3, [&](int r, int c, const float4& a) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[3] + c));
     *reinterpret_cast<float4*>(bufB + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
   });
@@ -74,7 +107,11 @@ __device__ __forceinline__ void critic_forward_tile(const float* __restrict__ cw
 // ------------------------------------------------------------------------------------------ critic
 template <int S>
 struct CriticSmem {
-  float XN[S][NSP], XNN[S][NSP], A0[S][NSP], G0[S][NSP];
+  alignas(128) float WB[2 * W_CHUNK];
+  uint64_t bar[2];
+  WeightSeq seq;
+  alignas(16) float XN[S][NSP];
+  float XNN[S][NSP], A0[S][NSP], G0[S][NSP];
   float SN[S][CW], CS[S][CW], G[S][CW], DL[S][CW], A[S][CW];
   float V[S], VT[S], VTN[S], Y[S], VBAR[S], WGT[S];
   float loss;
@@ -88,7 +125,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
                                                        const float* __restrict__ done, const float* __restrict__ weights, float inv_B,
                                                        float* __restrict__ grad, float* __restrict__ rtg_out, float* __restrict__ V_out,
                                                        float* __restrict__ Vt_out, float* __restrict__ loss_out, int64_t B) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   CriticSmem<S>& sm = *reinterpret_cast<CriticSmem<S>*>(smem_raw);
   const CriticLayout L(P.ns);
   const int ns = P.ns, nx = P.nx, tid = threadIdx.x;
@@ -96,14 +133,29 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   const int rows = (int)min((int64_t)S, B - row0);
   const bool sobolev = (w_S != 0.f);
 
+  WeightPipe pipe;
+  int gi = 0;
+  if (tid == 0) {
+    sm.seq.n = 0;
+    if (!mc) seq_push_critic_fwd(sm.seq, L, tw);
+    seq_push_critic_fwd(sm.seq, L, tw);
+    seq_push_critic_fwd(sm.seq, L, cw);
+    if (sobolev) {
+      seq_push_critic_bwd(sm.seq, L, cwT);
+      seq_push_critic_fwd(sm.seq, L, cw);
+    }
+    seq_push_critic_bwd(sm.seq, L, cwT);
+    sm.loss = 0.f;
+  }
+  pipe.init(sm.WB, sm.bar);
+  pipe.issue(sm.seq.ptr[0], sm.seq.first[0]);
   load_normalised<S>(P, state, row0, rows, sm.XN);
   if (!mc) load_normalised<S>(P, state_next, row0, rows, sm.XNN);
-  if (tid == 0) sm.loss = 0.f;
   __syncthreads();
 
   // ---- target critic: V_t(s_next) for the TD(n) tail (NeuralNetwork.py:157-158) and V_t(s) (:178)
-  if (!mc) critic_forward_tile<S>(tw, L, sm.XNN, &sm.A[0][0], &sm.DL[0][0], CW, sm.VTN);
-  critic_forward_tile<S>(tw, L, sm.XN, &sm.A[0][0], &sm.DL[0][0], CW, sm.VT);
+  if (!mc) critic_forward_tile<S>(pipe, sm, gi, tw, L, sm.XNN, &sm.A[0][0], &sm.DL[0][0], CW, sm.VTN);
+  critic_forward_tile<S>(pipe, sm, gi, tw, L, sm.XN, &sm.A[0][0], &sm.DL[0][0], CW, sm.VT);
   if (tid < S) {
     float y = 0.f, w = 0.f;
     if (tid < rows) {
@@ -132,11 +184,11 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   };
   tile_gemm<S, CR_H1, UP_NT, false>(&sm.XN[0][0], NSP, ns, cw + L.W[0], CR_H1, f_epi(0));
   __syncthreads();
-  tile_gemm<S, CR_H2, UP_NT, false>(&sm.SN[0][koff(0)], CW, CR_H1, cw + L.W[1], CR_H2, f_epi(1));
+  streamed<S, CR_H2>(pipe, sm, gi, &sm.SN[0][koff(0)], CW, CR_H1, f_epi(1));
   __syncthreads();
-  tile_gemm<S, CR_H3, UP_NT, false>(&sm.SN[0][koff(1)], CW, CR_H2, cw + L.W[2], CR_H3, f_epi(2));
+  streamed<S, CR_H3>(pipe, sm, gi, &sm.SN[0][koff(1)], CW, CR_H2, f_epi(2));
   __syncthreads();
-  tile_gemm<S, CR_H4, UP_NT, false>(&sm.SN[0][koff(2)], CW, CR_H3, cw + L.W[3], CR_H4, f_epi(3));
+  streamed<S, CR_H4>(pipe, sm, gi, &sm.SN[0][koff(2)], CW, CR_H3, f_epi(3));
   __syncthreads();
   tile_gemm_small<S, UP_NT, 8, true>(&sm.SN[0][koff(3)], CW, CR_H4, cw + L.W[4], 1, 0,
                                      [&](int s, int, float v) { sm.V[s] = v + __ldg(cw + L.b[4]); });
@@ -159,11 +211,11 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
         *reinterpret_cast<float4*>(&sm.DL[r][koff(l) + c]) = make_float4(a.x * co.x, a.y * co.y, a.z * co.z, a.w * co.w);
       };
     };
-    tile_gemm<S, CR_H3, UP_NT, false>(&sm.DL[0][koff(3)], CW, CR_H4, cwT + L.W[3], CR_H3, g_epi(2));
+    streamed<S, CR_H3>(pipe, sm, gi, &sm.DL[0][koff(3)], CW, CR_H4, g_epi(2));
     __syncthreads();
-    tile_gemm<S, CR_H2, UP_NT, false>(&sm.DL[0][koff(2)], CW, CR_H3, cwT + L.W[2], CR_H2, g_epi(1));
+    streamed<S, CR_H2>(pipe, sm, gi, &sm.DL[0][koff(2)], CW, CR_H3, g_epi(1));
     __syncthreads();
-    tile_gemm<S, CR_H1, UP_NT, false>(&sm.DL[0][koff(1)], CW, CR_H2, cwT + L.W[1], CR_H1, g_epi(0));
+    streamed<S, CR_H1>(pipe, sm, gi, &sm.DL[0][koff(1)], CW, CR_H2, g_epi(0));
     __syncthreads();
     tile_gemm_small<S, UP_NT, 8, false>(&sm.DL[0][koff(0)], CW, CR_H1, cw + L.W[0], ns, CR_H1,
                                         [&](int s, int j, float v) { sm.G0[s][j] = v; });
@@ -218,11 +270,11 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
     };
     tile_gemm<S, CR_H1, UP_NT, false>(&sm.A0[0][0], NSP, ns, cw + L.W[0], CR_H1, a_epi(0));
     __syncthreads();
-    tile_gemm<S, CR_H2, UP_NT, false>(&sm.A[0][koff(0)], CW, CR_H1, cw + L.W[1], CR_H2, a_epi(1));
+    streamed<S, CR_H2>(pipe, sm, gi, &sm.A[0][koff(0)], CW, CR_H1, a_epi(1));
     __syncthreads();
-    tile_gemm<S, CR_H3, UP_NT, false>(&sm.A[0][koff(1)], CW, CR_H2, cw + L.W[2], CR_H3, a_epi(2));
+    streamed<S, CR_H3>(pipe, sm, gi, &sm.A[0][koff(1)], CW, CR_H2, a_epi(2));
     __syncthreads();
-    tile_gemm<S, CR_H4, UP_NT, false>(&sm.A[0][koff(2)], CW, CR_H3, cw + L.W[3], CR_H4, a_epi(3));
+    streamed<S, CR_H4>(pipe, sm, gi, &sm.A[0][koff(2)], CW, CR_H3, a_epi(3));
     __syncthreads();
     tile_colsum<UP_NT>(&sm.A[0][koff(3)], CW, CR_H4, rows, grad + L.W[4]);       // d w5 += sum_s a_4
   } else {
@@ -259,19 +311,19 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   tile_outer2<S, CR_H4, UP_NT>(&sm.SN[0][koff(2)], CW, &sm.G[0][koff(3)], CW, A2 ? A2 + koff(2) : nullptr, CW, &sm.DL[0][koff(3)], CW,
                                CR_H3, grad + L.W[3], rows);
   tile_colsum<UP_NT>(&sm.G[0][koff(3)], CW, CR_H4, rows, grad + L.b[3]);
-  tile_gemm<S, CR_H3, UP_NT, false>(&sm.G[0][koff(3)], CW, CR_H4, cwT + L.W[3], CR_H3, b_epi(2));
+  streamed<S, CR_H3>(pipe, sm, gi, &sm.G[0][koff(3)], CW, CR_H4, b_epi(2));
   __syncthreads();
   // layer 3
   tile_outer2<S, CR_H3, UP_NT>(&sm.SN[0][koff(1)], CW, &sm.G[0][koff(2)], CW, A2 ? A2 + koff(1) : nullptr, CW, &sm.DL[0][koff(2)], CW,
                                CR_H2, grad + L.W[2], rows);
   tile_colsum<UP_NT>(&sm.G[0][koff(2)], CW, CR_H3, rows, grad + L.b[2]);
-  tile_gemm<S, CR_H2, UP_NT, false>(&sm.G[0][koff(2)], CW, CR_H3, cwT + L.W[2], CR_H2, b_epi(1));
+  streamed<S, CR_H2>(pipe, sm, gi, &sm.G[0][koff(2)], CW, CR_H3, b_epi(1));
   __syncthreads();
   // layer 2
   tile_outer2<S, CR_H2, UP_NT>(&sm.SN[0][koff(0)], CW, &sm.G[0][koff(1)], CW, A2 ? A2 + koff(0) : nullptr, CW, &sm.DL[0][koff(1)], CW,
                                CR_H1, grad + L.W[1], rows);
   tile_colsum<UP_NT>(&sm.G[0][koff(1)], CW, CR_H2, rows, grad + L.b[1]);
-  tile_gemm<S, CR_H1, UP_NT, false>(&sm.G[0][koff(1)], CW, CR_H2, cwT + L.W[1], CR_H1, b_epi(0));
+  streamed<S, CR_H1>(pipe, sm, gi, &sm.G[0][koff(1)], CW, CR_H2, b_epi(0));
   __syncthreads();
   // layer 1
   tile_outer2<S, CR_H1, UP_NT>(&sm.XN[0][0], NSP, &sm.G[0][koff(0)], CW, sobolev ? &sm.A0[0][0] : nullptr, NSP, &sm.DL[0][koff(0)], CW, ns,
@@ -282,7 +334,11 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
 // ------------------------------------------------------------------------------------------ actor
 template <int S>
 struct ActorSmem {
-  float XN[S][NSP], XNP[S][NSP], G0[S][NSP];
+  alignas(128) float WB[2 * W_CHUNK];
+  uint64_t bar[2];
+  WeightSeq seq;
+  alignas(16) float XN[S][NSP];
+  float XNP[S][NSP], G0[S][NSP];
   float H1[S][ACTOR_H], H2[S][ACTOR_H], E[S][ACTOR_H];
   float CS[S][CW];
   float CH[2][S][CR_H4];
@@ -298,7 +354,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
                                                       const double* __restrict__ term, float inv_B, float* __restrict__ grad,
                                                       float* __restrict__ actions_out, int64_t B) {
   constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA, NS = NX + 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   ActorSmem<S>& sm = *reinterpret_cast<ActorSmem<S>*>(smem_raw);
   const ActorLayout LA(NS, NA);
   const CriticLayout LC(NS);
@@ -306,6 +362,17 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
   const int64_t row0 = (int64_t)blockIdx.x * S;
   const int rows = (int)min((int64_t)S, B - row0);
 
+  WeightPipe pipe;
+  int gi = 0;
+  if (tid == 0) {
+    sm.seq.n = 0;
+    seq_push<ACTOR_H>(sm.seq, aw + LA.W2, ACTOR_H);
+    seq_push_critic_fwd(sm.seq, LC, cw);
+    seq_push_critic_bwd(sm.seq, LC, cwT);
+    seq_push<ACTOR_H>(sm.seq, awT + LA.W2, ACTOR_H);
+  }
+  pipe.init(sm.WB, sm.bar);
+  pipe.issue(sm.seq.ptr[0], sm.seq.first[0]);
   load_normalised<S>(P, state, row0, rows, sm.XN);
   __syncthreads();
   // ---- actor forward (NeuralNetwork.py:185)
@@ -314,7 +381,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
     *reinterpret_cast<float4*>(&sm.H1[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
   });
   __syncthreads();
-  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.H1[0][0], ACTOR_H, ACTOR_H, aw + LA.W2, ACTOR_H, [&](int r, int c, const float4& a) {
+  streamed<S, ACTOR_H>(pipe, sm, gi, &sm.H1[0][0], ACTOR_H, ACTOR_H, [&](int r, int c, const float4& a) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(aw + LA.b2 + c));
     *reinterpret_cast<float4*>(&sm.H2[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
   });
@@ -382,11 +449,11 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
   float* ch1 = &sm.CH[1][0][0];
   tile_gemm<S, CR_H1, UP_NT, false>(&sm.XNP[0][0], NSP, NS, cw + LC.W[0], CR_H1, cf_epi(0, ch0));
   __syncthreads();
-  tile_gemm<S, CR_H2, UP_NT, false>(ch0, CR_H4, CR_H1, cw + LC.W[1], CR_H2, cf_epi(1, ch1));
+  streamed<S, CR_H2>(pipe, sm, gi, ch0, CR_H4, CR_H1, cf_epi(1, ch1));
   __syncthreads();
-  tile_gemm<S, CR_H3, UP_NT, false>(ch1, CR_H4, CR_H2, cw + LC.W[2], CR_H3, cf_epi(2, ch0));
+  streamed<S, CR_H3>(pipe, sm, gi, ch1, CR_H4, CR_H2, cf_epi(2, ch0));
   __syncthreads();
-  tile_gemm<S, CR_H4, UP_NT, false>(ch0, CR_H4, CR_H3, cw + LC.W[3], CR_H4, cf_epi(3, ch1));
+  streamed<S, CR_H4>(pipe, sm, gi, ch0, CR_H4, CR_H3, cf_epi(3, ch1));
   __syncthreads();
   float* dl0 = &sm.DLp[0][0][0];
   float* dl1 = &sm.DLp[1][0][0];
@@ -401,11 +468,11 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
       *reinterpret_cast<float4*>(out + r * CR_H4 + c) = make_float4(a.x * co.x, a.y * co.y, a.z * co.z, a.w * co.w);
     };
   };
-  tile_gemm<S, CR_H3, UP_NT, false>(dl0, CR_H4, CR_H4, cwT + LC.W[3], CR_H3, cg_epi(2, dl1));
+  streamed<S, CR_H3>(pipe, sm, gi, dl0, CR_H4, CR_H4, cg_epi(2, dl1));
   __syncthreads();
-  tile_gemm<S, CR_H2, UP_NT, false>(dl1, CR_H4, CR_H3, cwT + LC.W[2], CR_H2, cg_epi(1, dl0));
+  streamed<S, CR_H2>(pipe, sm, gi, dl1, CR_H4, CR_H3, cg_epi(1, dl0));
   __syncthreads();
-  tile_gemm<S, CR_H1, UP_NT, false>(dl0, CR_H4, CR_H2, cwT + LC.W[1], CR_H1, cg_epi(0, dl1));
+  streamed<S, CR_H1>(pipe, sm, gi, dl0, CR_H4, CR_H2, cg_epi(0, dl1));
   __syncthreads();
   tile_gemm_small<S, UP_NT, 8, false>(dl1, CR_H4, CR_H1, cw + LC.W[0], NS, CR_H1, [&](int s, int j, float v) { sm.G0[s][j] = v; });
   __syncthreads();
@@ -446,7 +513,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
   __syncthreads();
   tile_outer2<S, ACTOR_H, UP_NT>(&sm.H1[0][0], ACTOR_H, &sm.E[0][0], ACTOR_H, nullptr, 0, nullptr, 0, ACTOR_H, grad + LA.W2, rows);
   tile_colsum<UP_NT>(&sm.E[0][0], ACTOR_H, ACTOR_H, rows, grad + LA.b2);
-  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.E[0][0], ACTOR_H, ACTOR_H, awT + LA.W2, ACTOR_H, [&](int r, int c, const float4& a) {
+  streamed<S, ACTOR_H>(pipe, sm, gi, &sm.E[0][0], ACTOR_H, ACTOR_H, [&](int r, int c, const float4& a) {
     const float4 h = *reinterpret_cast<const float4*>(&sm.H1[r][c]);
     *reinterpret_cast<float4*>(&sm.H2[r][c]) =
         make_float4(a.x * (h.x > 0.f ? 1.f : LEAKY_ALPHA), a.y * (h.y > 0.f ? 1.f : LEAKY_ALPHA), a.z * (h.z > 0.f ? 1.f : LEAKY_ALPHA),
@@ -460,7 +527,10 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
 // ------------------------------------------------------------------------------------------ forward-only kernels
 template <int S>
 struct EvalSmem {
-  float XN[S][NSP];
+  alignas(128) float WB[2 * W_CHUNK];
+  uint64_t bar[2];
+  WeightSeq seq;
+  alignas(16) float XN[S][NSP];
   float A[S][ACTOR_H], Bf[S][ACTOR_H];
   float CS[S][CW];
   float V[S], G0[S][NSP];
@@ -470,12 +540,20 @@ struct EvalSmem {
 template <int S>
 __global__ void __launch_bounds__(UP_NT) k_actor_forward(const __grid_constant__ cacto_sys_params P, const float* __restrict__ aw,
                                                          const float* __restrict__ state, float* __restrict__ out, int64_t B) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   EvalSmem<S>& sm = *reinterpret_cast<EvalSmem<S>*>(smem_raw);
   const int ns = P.ns, na = P.na;
   const ActorLayout LA(ns, na);
   const int64_t row0 = (int64_t)blockIdx.x * S;
   const int rows = (int)min((int64_t)S, B - row0);
+  WeightPipe pipe;
+  int gi = 0;
+  if (threadIdx.x == 0) {
+    sm.seq.n = 0;
+    seq_push<ACTOR_H>(sm.seq, aw + LA.W2, ACTOR_H);
+  }
+  pipe.init(sm.WB, sm.bar);
+  pipe.issue(sm.seq.ptr[0], sm.seq.first[0]);
   load_normalised<S>(P, state, row0, rows, sm.XN);
   __syncthreads();
   tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.XN[0][0], NSP, ns, aw + LA.W1, ACTOR_H, [&](int r, int c, const float4& a) {
@@ -483,7 +561,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_forward(const __grid_constant__
     *reinterpret_cast<float4*>(&sm.A[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
   });
   __syncthreads();
-  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.A[0][0], ACTOR_H, ACTOR_H, aw + LA.W2, ACTOR_H, [&](int r, int c, const float4& a) {
+  streamed<S, ACTOR_H>(pipe, sm, gi, &sm.A[0][0], ACTOR_H, ACTOR_H, [&](int r, int c, const float4& a) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(aw + LA.b2 + c));
     *reinterpret_cast<float4*>(&sm.Bf[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
   });
@@ -497,12 +575,20 @@ template <int S>
 __global__ void __launch_bounds__(UP_NT) k_critic_forward(const __grid_constant__ cacto_sys_params P, const float* __restrict__ cw,
                                                           const float* __restrict__ state, float* __restrict__ value,
                                                           float* __restrict__ dV_ds, int64_t B) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   EvalSmem<S>& sm = *reinterpret_cast<EvalSmem<S>*>(smem_raw);
   const int ns = P.ns, tid = threadIdx.x;
   const CriticLayout L(ns);
   const int64_t row0 = (int64_t)blockIdx.x * S;
   const int rows = (int)min((int64_t)S, B - row0);
+  WeightPipe pipe;
+  int gi = 0;
+  if (tid == 0) {
+    sm.seq.n = 0;
+    seq_push_critic_fwd(sm.seq, L, cw);
+  }
+  pipe.init(sm.WB, sm.bar);
+  pipe.issue(sm.seq.ptr[0], sm.seq.first[0]);
   load_normalised<S>(P, state, row0, rows, sm.XN);
   __syncthreads();
   float* bufA = &sm.A[0][0];
@@ -521,11 +607,11 @@ __global__ void __launch_bounds__(UP_NT) k_critic_forward(const __grid_constant_
   };
   tile_gemm<S, CR_H1, UP_NT, false>(&sm.XN[0][0], NSP, ns, cw + L.W[0], CR_H1, f_epi(0, bufA));
   __syncthreads();
-  tile_gemm<S, CR_H2, UP_NT, false>(bufA, ACTOR_H, CR_H1, cw + L.W[1], CR_H2, f_epi(1, bufB));
+  streamed<S, CR_H2>(pipe, sm, gi, bufA, ACTOR_H, CR_H1, f_epi(1, bufB));
   __syncthreads();
-  tile_gemm<S, CR_H3, UP_NT, false>(bufB, ACTOR_H, CR_H2, cw + L.W[2], CR_H3, f_epi(2, bufA));
+  streamed<S, CR_H3>(pipe, sm, gi, bufB, ACTOR_H, CR_H2, f_epi(2, bufA));
   __syncthreads();
-  tile_gemm<S, CR_H4, UP_NT, false>(bufA, ACTOR_H, CR_H3, cw + L.W[3], CR_H4, f_epi(3, bufB));
+  streamed<S, CR_H4>(pipe, sm, gi, bufA, ACTOR_H, CR_H3, f_epi(3, bufB));
   __syncthreads();
   tile_gemm_small<S, UP_NT, 8, true>(bufB, ACTOR_H, CR_H4, cw + L.W[4], 1, 0, [&](int s, int, float v) {
     if (s < rows) value[row0 + s] = v + __ldg(cw + L.b[4]);
@@ -562,7 +648,8 @@ struct LayerTable {
 
 // p -= alpha * m / (sqrt(v) + eps) with m += (g - m)(1 - b1), v += (g^2 - v)(1 - b2)   
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                              float alpha, float omb1, float omb2, float eps, float* __restrict__ target, float tau,
+                                              float alpha, const float* __restrict__ alpha_dev, float omb1, float omb2, float eps,
+                                              float* __restrict__ target, float tau,
                                               float* __restrict__ pT, LayerTable T, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -573,6 +660,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __re
   vi += (gi * gi - vi) * omb2;
   m[i] = mi;
   v[i] = vi;
+  if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);     // device-side schedule (CUDA-graph replays)
   const float pi = p[i] - (mi * alpha) / (sqrtf(vi) + eps);
   p[i] = pi;
   if (target != nullptr) target[i] = pi * tau + target[i] * (1.f - tau);      // RL.py:116-118
@@ -735,14 +823,38 @@ extern "C" int cacto_critic_forward(const cacto_sys_params* p, const float* crit
   return 0;
 }
 
-extern "C" int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_t, float beta1, float beta2, float eps,
+// alpha_t = lr(step) sqrt(1 - b2^t) / (1 - b1^t), t = step + 1, evaluated on the device so that a captured
+// CUDA graph of the update can be replayed without host-side scalars.  Also clears `zero_me` (loss accumulator).
+__global__ void k_adam_schedule(long long* __restrict__ step, const float* __restrict__ boundaries, const float* __restrict__ values,
+                                int nb, float beta1, float beta2, float* __restrict__ alpha_out, float* __restrict__ zero_me) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long it = step[0];
+  int k = 0;
+  for (int i = 0; i < nb; ++i) k += (boundaries[i] < (float)it) ? 1 : 0;        // PiecewiseConstantDecay: values[#{b < step}]
+  const float lr = values[k];
+  const float t = (float)(it + 1);
+  alpha_out[0] = lr * sqrtf(1.f - powf(beta2, t)) / (1.f - powf(beta1, t));
+  step[0] = it + 1;
+  if (zero_me != nullptr) zero_me[0] = 0.f;
+}
+
+extern "C" int cacto_adam_schedule(int64_t* step, const float* boundaries, const float* values, int32_t nb, float beta1, float beta2,
+                                   float* alpha_out, float* zero_or_null, void* stream) {
+  if (!step || !values || !alpha_out || (nb > 0 && !boundaries) || nb < 0) return CACTO_E_ARG;
+  k_adam_schedule<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(step), boundaries, values, nb, beta1, beta2, alpha_out,
+                                                      zero_or_null);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_t, const float* alpha_dev_or_null, float beta1, float beta2, float eps,
                                float* target_or_null, float tau, float* params_T_or_null, int32_t is_critic, int32_t ns, int32_t na,
                                int64_t n, void* stream) {
   if (!params || !grad || !m || !v) return CACTO_E_ARG;
   int64_t total = 0;
   LayerTable T = make_table(is_critic, ns, na, &total);
   if (n != total) return CACTO_E_SIZE;
-  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, m, v, alpha_t, 1.f - beta1, 1.f - beta2, eps,
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, m, v, alpha_t, alpha_dev_or_null, 1.f - beta1, 1.f - beta2, eps,
                                                                        target_or_null, tau, params_T_or_null, T, n);
   CACTO_LAUNCH_CHECK();
   return 0;

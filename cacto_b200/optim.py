@@ -3,7 +3,10 @@
 Reference use: RL.py:82-88 (construction, optional schedule), :105,:109 (apply_gradients).
 TF-2.11 update (SURVEY.md A.5): t = iterations + 1; alpha_t = lr(iterations) sqrt(1 - b2^t) / (1 - b1^t);
 m += (g - m)(1 - b1); v += (g^2 - v)(1 - b2); p -= alpha_t m / (sqrt(v) + eps), eps = 1e-7 un-corrected.
-alpha_t is evaluated on the host in float32 like TF does on its float32 variables.
+
+alpha_t is evaluated on the device (``cacto_adam_schedule``: step counter, schedule table and alpha live in
+HBM) so that a captured CUDA graph of the whole update replays without host-side scalars; ``iterations`` on
+the host mirrors the device counter.
 """
 import numpy as np
 import torch
@@ -28,26 +31,40 @@ class Adam:
         self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
         self.iterations = 0
         self._state = {}
+        self._dev = None
 
     def current_lr(self):
         return self.learning_rate(self.iterations) if callable(self.learning_rate) else self.learning_rate
 
-    def _alpha(self):
-        f = np.float32
-        t = f(self.iterations + 1)
-        return float(f(self.current_lr()) * np.sqrt(f(1) - np.power(f(self.beta_2), t)) / (f(1) - np.power(f(self.beta_1), t)))
+    def _device_state(self, device):
+        if self._dev is None:
+            if isinstance(self.learning_rate, PiecewiseConstantDecay):
+                b, v = self.learning_rate.boundaries, self.learning_rate.values
+            elif callable(self.learning_rate):
+                raise TypeError('only float or PiecewiseConstantDecay learning rates are supported')
+            else:
+                b, v = [], [self.learning_rate]
+            self._dev = dict(step=torch.full((1,), self.iterations, dtype=torch.int64, device=device),
+                             alpha=torch.zeros(1, dtype=torch.float32, device=device),
+                             boundaries=torch.tensor(b if b else [0.0], dtype=torch.float32, device=device),
+                             values=torch.tensor(v, dtype=torch.float32, device=device), nb=len(b))
+        return self._dev
 
-    def step(self, net, target=None, tau=0.0):
+    def step(self, net, target=None, tau=0.0, zero=None):
         """One Adam step on ``net`` from ``net.grad`` (zeroed afterwards); optionally the Polyak update
-        ``target = tau * net + (1 - tau) * target`` (RL.py:113-118) in the same launch."""
+        ``target = tau * net + (1 - tau) * target`` (RL.py:113-118) in the same launch.  ``zero`` is an optional
+        one-element float tensor cleared by the schedule kernel (the loss accumulator)."""
         st = self._state.get(id(net))
         if st is None:
             st = (torch.zeros_like(net.params), torch.zeros_like(net.params))
             self._state[id(net)] = st
         m, v = st
-        check(lib.cacto_adam_step(ptr(net.params), ptr(net.grad), ptr(m), ptr(v), self._alpha(), self.beta_1, self.beta_2, self.epsilon,
-                                  ptr(target.params if target is not None else None), float(tau), ptr(net.params_T), net.is_critic,
-                                  net.ns, net.na, net.n, stream_ptr()), 'adam_step')
+        d = self._device_state(net.params.device)
+        check(lib.cacto_adam_schedule(ptr(d['step']), ptr(d['boundaries']), ptr(d['values']), d['nb'], self.beta_1, self.beta_2,
+                                      ptr(d['alpha']), ptr(zero), stream_ptr()), 'adam_schedule')
+        check(lib.cacto_adam_step(ptr(net.params), ptr(net.grad), ptr(m), ptr(v), 0.0, ptr(d['alpha']), self.beta_1, self.beta_2,
+                                  self.epsilon, ptr(target.params if target is not None else None), float(tau), ptr(net.params_T),
+                                  net.is_critic, net.ns, net.na, net.n, stream_ptr()), 'adam_step')
         self.iterations += 1
 
     def apply_gradients(self, grads_and_vars):

@@ -143,9 +143,15 @@ int cacto_actor_grad(const cacto_sys_params* p, const float* actor_params, const
  *      target = tau p + (1-tau) target), the refresh of the transposed copy and the zeroing of `grad`.
  *      alpha_t = lr(t-1) sqrt(1-b2^t)/(1-b1^t) is computed by the caller. n must equal the network's
  *      parameter count. */
-int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_t, float beta1, float beta2,
-                    float eps, float* target_or_null, float tau, float* params_T_or_null, int32_t is_critic,
-                    int32_t ns, int32_t na, int64_t n, void* stream);
+int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_t, const float* alpha_dev_or_null,
+                    float beta1, float beta2, float eps, float* target_or_null, float tau, float* params_T_or_null,
+                    int32_t is_critic, int32_t ns, int32_t na, int64_t n, void* stream);
+
+/* Device-side learning-rate schedule for CUDA-graph replays of the update: reads the step counter, writes
+ * alpha_out[0] = values[#{boundaries < step}] sqrt(1-b2^t)/(1-b1^t) with t = step+1 (PiecewiseConstantDecay,
+ * RL.py:82-85; nb = 0 for a constant rate values[0]), increments the counter and clears zero_or_null[0]. */
+int cacto_adam_schedule(int64_t* step, const float* boundaries, const float* values, int32_t nb, float beta1,
+                        float beta2, float* alpha_out, float* zero_or_null, void* stream);
 
 /* Rebuild the per-layer transposed copy of a parameter block (W^T per layer, biases copied). */
 int cacto_transpose_params(const float* params, float* params_T, int32_t is_critic, int32_t ns, int32_t na,
@@ -187,6 +193,10 @@ int cacto_buffer_gather(const double* storage, int32_t ns, const int64_t* idx, i
 int cacto_rtg_window(const int64_t* offsets, int32_t E, const double* rwrd, const double* states, int32_t ns,
                      int32_t nsteps_td, int32_t mc, double* partial, double* total_rtg, double* s_next,
                      double* done, double* term, double* ep_return, void* stream);
+
+/* ---- measurement only (bench.py): blocks x 256 threads each issue iters x 16 independent-chain fp32 FMAs;
+ *      flops = blocks * 256 * iters * 16 * 2.  The in-run FP32-FMA roofline denominator. */
+int cacto_peak_fma_fp32(float* out, int32_t iters, int32_t blocks, void* stream);
 
 #ifdef __cplusplus
 }
