@@ -288,6 +288,30 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         up_ms = float(t[0])
     updates_per_s = n_up / (up_ms * 1e-3)
+    # the same update replayed as a CUDA graph (6 kernel nodes + NCCL all-reduces when world > 1)
+    graph_updates_per_s = None
+    try:
+        ug = rl.make_update_graph(Bu)
+        for k_, t_ in (('state', s), ('state_next', sn), ('partial_rtg', pr), ('dVdx', dv), ('done', d), ('term', term), ('weights', w)):
+            ug.io[k_].copy_(t_)
+        for _ in range(20):
+            ug.replay()
+        barrier()
+        n_gr = 1000
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n_gr):
+            ug.replay()
+        b.record(stream)
+        torch.cuda.synchronize()
+        gr_ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([gr_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gr_ms = float(t[0])
+        graph_updates_per_s = n_gr / (gr_ms * 1e-3)
+    except Exception as exc:           # report, do not hide
+        graph_updates_per_s = f'failed: {type(exc).__name__}: {exc}'
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -313,7 +337,7 @@ def run_b200(args):
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': K,
             'clocks': clocks,
-            'extra': {'sobolev_updates_per_s': updates_per_s, 'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world,
+            'extra': {'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s, 'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world,
                       'update_launches_per_update': 4, 'fp32_fma_peak_tflops_measured': fma_peak_tflops},
         }
         if cpu is not None:

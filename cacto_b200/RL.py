@@ -19,6 +19,7 @@ import torch
 from ._lib import check, lib, ptr, stream_ptr
 from .environment import _as_cuda, _device
 from .optim import Adam, PiecewiseConstantDecay
+from .parallel import allreduce_sum
 from .rtg import rtg_batch as _rtg_batch
 
 
@@ -81,8 +82,7 @@ class RL_AC:
 
     # ------------------------------------------------------------------------------ update
     def _allreduce(self, net):
-        if self.dist is not None and self.dist.get_world_size() > 1:
-            self.dist.all_reduce(net.grad)             # NCCL sum over NVLink; each rank used 1/global_batch
+        allreduce_sum(net.grad, self.dist)             # NCCL sum over NVLink; each rank used 1/global_batch
 
     def update(self, state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
                batch_size=None, fuse_target=False):
@@ -105,6 +105,37 @@ class RL_AC:
         self.actor_optimizer.apply_gradients(zip(actor_grad, self.actor_model.trainable_variables))
         return reward_to_go_batch, critic_value, target_critic_value
 
+    # ------------------------------------------------------------------------------ CUDA-graph update
+    def _update_static(self, io):
+        """The launches of one update + target update on pre-allocated tensors (no allocation, no host scalars):
+        what ``make_update_graph`` captures.  Gradient accumulators are left zeroed by the Adam kernel."""
+        c, nn = self.conf, self.NN
+        world = self.dist.get_world_size() if self.dist is not None else 1
+        B = io['state'].shape[0]
+        inv_B = 1.0 / float(B * world)
+        cm, tc, am = self.critic_model, self.target_critic, self.actor_model
+        self.critic_optimizer.prepare(cm.params.device, zero=nn.last_critic_loss)
+        check(lib.cacto_critic_grad(self.env._p, ptr(cm.params), ptr(cm.params_T), ptr(tc.params), float(nn.w_S), int(bool(c.MC)),
+                                    ptr(io['state']), ptr(io['state_next']), ptr(io['partial_rtg']), ptr(io['dVdx']), ptr(io['done']),
+                                    ptr(io['weights']), inv_B, ptr(cm.grad), ptr(io['rtg']), ptr(io['V']), ptr(io['V_target']),
+                                    ptr(nn.last_critic_loss), B, stream_ptr()), 'critic_grad')
+        self._allreduce(cm)
+        if c.MC:
+            self.critic_optimizer.step(cm, prepared=True)
+        else:
+            self.critic_optimizer.step(cm, target=tc, tau=c.UPDATE_RATE, prepared=True)
+        self.actor_optimizer.prepare(am.params.device)
+        check(lib.cacto_actor_grad(self.env._p, ptr(am.params), ptr(am.params_T), ptr(cm.params), ptr(cm.params_T), ptr(io['state']),
+                                   ptr(io['term']), inv_B, ptr(am.grad), ptr(None), B, stream_ptr()), 'actor_grad')
+        self._allreduce(am)
+        self.actor_optimizer.step(am, prepared=True)
+
+    def make_update_graph(self, batch_size=None):
+        """Capture update + update_target for a fixed batch size into a CUDA graph.  Returns an ``UpdateGraph`` whose
+        ``io`` tensors (state, state_next, partial_rtg, dVdx, done, term, weights -> rtg, V, V_target) are filled by
+        ``buffer.sample(out=graph.io)`` and whose ``replay()`` performs one update; training state is untouched by the capture."""
+        return UpdateGraph(self, int(batch_size or self.conf.BATCH_SIZE))
+
     def update_target(self, target_weights, weights):
         """RL.py:113-118: a <- b * tau + a * (1 - tau)."""
         tau = float(self.conf.UPDATE_RATE)
@@ -113,11 +144,16 @@ class RL_AC:
 
     def learn_and_update(self, update_step_counter, buffer, ep):
         """RL.py:120-143."""
+        graph = getattr(self, 'update_graph', None)
         for _ in range(int(self.conf.UPDATE_LOOPS[ep])):
-            state_batch, partial_reward_to_go_batch, state_next_rollout_batch, dVdx_batch, d_batch, term_batch, weights_batch, batch_idxes = buffer.sample()
-            reward_to_go_batch, critic_value, target_critic_value = self.update(
-                state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
-                fuse_target=True)
+            if graph is not None:                       # captured update: the sampled rows land in the graph's input tensors
+                batch_idxes = buffer.sample(out=graph.io)[7]
+                reward_to_go_batch, critic_value, target_critic_value = graph.replay()
+            else:
+                state_batch, partial_reward_to_go_batch, state_next_rollout_batch, dVdx_batch, d_batch, term_batch, weights_batch, batch_idxes = buffer.sample()
+                reward_to_go_batch, critic_value, target_critic_value = self.update(
+                    state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
+                    fuse_target=True)
             if self.conf.prioritized_replay_alpha != 0:
                 buffer.update_priorities(batch_idxes, reward_to_go_batch, critic_value, target_critic_value)
             update_step_counter += 1
@@ -234,3 +270,56 @@ class RL_AC:
         self.state_arr[0, :] = ICS
         self.ee_pos_arr[0, :] = self.env.get_end_effector_position(self.state_arr[0, :])
         return self.init_rand_state, init_TO_states, init_TO_controls, self.NSTEPS_SH, 1
+
+
+class UpdateGraph:
+    """One critic+actor update (RL.py:101-118) as a replayable CUDA graph: 6 kernel nodes
+    (schedule, critic gradient, critic Adam + Polyak, schedule, actor gradient, actor Adam), plus the NCCL
+    all-reduces when data-parallel.  At the reference's batch sizes (64/128) the update is launch-latency bound;
+    replaying a graph removes the per-launch host cost."""
+
+    def __init__(self, rl, B):
+        self.rl, self.B = rl, B
+        c = rl.conf
+        dev = _device()
+        ns = c.nb_state
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.io = dict(state=torch.zeros((B, ns), **f32), state_next=torch.zeros((B, ns), **f32), partial_rtg=torch.zeros((B, 1), **f32),
+                       dVdx=torch.zeros((B, ns), **f32), done=torch.zeros((B, 1), **f32), term=torch.zeros((B, 1), dtype=torch.float64, device=dev),
+                       weights=torch.ones((B, 1), **f32), rtg=torch.zeros((B, 1), **f32), V=torch.zeros((B, 1), **f32),
+                       V_target=torch.zeros((B, 1), **f32))
+        nets = (rl.actor_model, rl.critic_model, rl.target_critic)
+        opts = (rl.critic_optimizer, rl.actor_optimizer)
+        for o, n in ((rl.critic_optimizer, rl.critic_model), (rl.actor_optimizer, rl.actor_model)):
+            o.moments(n)
+            o._device_state(dev)
+        for n in nets:
+            n.grad.zero_()
+        # snapshot the training state, warm up on a side stream (lazy initialisation), capture, restore
+        snap = [(t, t.clone()) for n in nets for t in (n.params, n.params_T)]
+        snap += [(t, t.clone()) for o in opts for st in o._state.values() for t in st]
+        snap += [(o._dev['step'], o._dev['step'].clone()) for o in opts]
+        its = [o.iterations for o in opts]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                rl._update_static(self.io)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            rl._update_static(self.io)
+        for t, old in snap:
+            t.copy_(old)
+        for o, it in zip(opts, its):
+            o.iterations = it
+        for n in nets:
+            n.grad.zero_()
+        torch.cuda.synchronize()
+
+    def replay(self):
+        self.graph.replay()
+        self.rl.critic_optimizer.iterations += 1
+        self.rl.actor_optimizer.iterations += 1
+        return self.io['rtg'], self.io['V'], self.io['V_target']

@@ -50,18 +50,27 @@ class Adam:
                              values=torch.tensor(v, dtype=torch.float32, device=device), nb=len(b))
         return self._dev
 
-    def step(self, net, target=None, tau=0.0, zero=None):
-        """One Adam step on ``net`` from ``net.grad`` (zeroed afterwards); optionally the Polyak update
-        ``target = tau * net + (1 - tau) * target`` (RL.py:113-118) in the same launch.  ``zero`` is an optional
-        one-element float tensor cleared by the schedule kernel (the loss accumulator)."""
+    def moments(self, net):
         st = self._state.get(id(net))
         if st is None:
             st = (torch.zeros_like(net.params), torch.zeros_like(net.params))
             self._state[id(net)] = st
-        m, v = st
-        d = self._device_state(net.params.device)
+        return st
+
+    def prepare(self, device, zero=None):
+        """Launch the schedule kernel: alpha_t for the coming step, step counter += 1, ``zero[0] = 0``
+        (an optional one-element float tensor, e.g. the loss accumulator the next kernel adds into)."""
+        d = self._device_state(device)
         check(lib.cacto_adam_schedule(ptr(d['step']), ptr(d['boundaries']), ptr(d['values']), d['nb'], self.beta_1, self.beta_2,
                                       ptr(d['alpha']), ptr(zero), stream_ptr()), 'adam_schedule')
+
+    def step(self, net, target=None, tau=0.0, prepared=False):
+        """One Adam step on ``net`` from ``net.grad`` (zeroed afterwards); optionally the Polyak update
+        ``target = tau * net + (1 - tau) * target`` (RL.py:113-118) in the same launch."""
+        m, v = self.moments(net)
+        if not prepared:
+            self.prepare(net.params.device)
+        d = self._device_state(net.params.device)
         check(lib.cacto_adam_step(ptr(net.params), ptr(net.grad), ptr(m), ptr(v), 0.0, ptr(d['alpha']), self.beta_1, self.beta_2,
                                   self.epsilon, ptr(target.params if target is not None else None), float(tau), ptr(net.params_T),
                                   net.is_critic, net.ns, net.na, net.n, stream_ptr()), 'adam_step')

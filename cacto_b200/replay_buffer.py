@@ -68,24 +68,32 @@ class ReplayBuffer(object):
     def _max_idx(self):
         return self.conf.REPLAY_SIZE if self.full else self.next_idx
 
-    def _gather(self, idx_dev):
+    def _gather(self, idx_dev, out=None):
         n, ns, dev = idx_dev.numel(), self.ns, self.storage_mat.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        s, r, s1, dv, d = (torch.empty((n, ns), **f32), torch.empty((n, 1), **f32), torch.empty((n, ns), **f32),
-                           torch.empty((n, ns), **f32), torch.empty((n, 1), **f32))
-        term = torch.empty((n, 1), dtype=torch.float64, device=dev)
+        if out is not None:          # pre-allocated tensors of a captured update graph (RL.UpdateGraph.io)
+            s, r, s1, dv, d, term = out['state'], out['partial_rtg'], out['state_next'], out['dVdx'], out['done'], out['term']
+            assert s.shape == (n, ns)
+        else:
+            f32 = dict(dtype=torch.float32, device=dev)
+            s, r, s1, dv, d = (torch.empty((n, ns), **f32), torch.empty((n, 1), **f32), torch.empty((n, ns), **f32),
+                               torch.empty((n, ns), **f32), torch.empty((n, 1), **f32))
+            term = torch.empty((n, 1), dtype=torch.float64, device=dev)
         check(lib.cacto_buffer_gather(ptr(self.storage_mat), ns, ptr(idx_dev), n, ptr(s), ptr(r), ptr(s1), ptr(dv), ptr(d),
                                       ptr(term), ptr(None), ptr(None), stream_ptr()), 'buffer_gather')
         return s, r, s1, dv, d, term
 
-    def sample(self, idxes=None):
+    def sample(self, idxes=None, out=None):
         """replay_buffer.py:38-61.  ``idxes`` may be injected (the reference draws them from the global,
-        unseeded ``np.random``: quirk Q5)."""
+        unseeded ``np.random``: quirk Q5); ``out`` = pre-allocated tensors to fill (RL.UpdateGraph.io)."""
         if idxes is None:
             idxes = np.random.randint(0, self._max_idx(), size=self.conf.BATCH_SIZE)
-        idx_dev = torch.as_tensor(np.asarray(idxes, dtype=np.int64)).to(self.storage_mat.device)
-        s, r, s1, dv, d, term = self._gather(idx_dev)
-        weights = torch.ones((idx_dev.numel(), 1), dtype=torch.float32, device=s.device)
+        idx_dev = torch.as_tensor(np.asarray(idxes, dtype=np.int64)).to(self.storage_mat.device, non_blocking=True)
+        s, r, s1, dv, d, term = self._gather(idx_dev, out)
+        if out is not None:
+            out['weights'].fill_(1.0)
+            weights = out['weights']
+        else:
+            weights = torch.ones((idx_dev.numel(), 1), dtype=torch.float32, device=s.device)
         return s, r, s1, dv, d, term, weights, None
 
 
@@ -137,12 +145,12 @@ class PrioritizedReplayBuffer(ReplayBuffer):
                                        ptr(idx), ptr(leaf), ptr(self._totals), stream_ptr()), 'segtree_sample')
         return idx, leaf
 
-    def sample(self, uniforms=None):
+    def sample(self, uniforms=None, out=None):
         """replay_buffer.py:159-188."""
         max_idx = self._max_idx()
         beta = self.conf.prioritized_replay_beta
         idx_dev, leaf_dev = self._sample_proportional(uniforms)
-        s, r, s1, dv, d, term = self._gather(idx_dev)
+        s, r, s1, dv, d, term = self._gather(idx_dev, out)
         # one small D2H: B indices + B leaves + 3 totals; the pow() below must be the host's (bit-exactness)
         batch_idxes = idx_dev.cpu().numpy().astype(int)
         leaf = leaf_dev.cpu().numpy()
@@ -153,6 +161,9 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         self.priorities[batch_idxes] = leaf / tot
         weights = (self.priorities[batch_idxes] * max_idx) ** (-beta) / max_weight
         weights = torch.as_tensor(weights.astype(np.float32)).to(s.device)
+        if out is not None:
+            out['weights'].copy_(weights.reshape(-1, 1))
+            weights = out['weights']
         return s, r, s1, dv, d, term, weights, batch_idxes
 
     def update_priorities(self, idxes, reward_to_go_batch, critic_value, target_critic_value=None):

@@ -1,0 +1,86 @@
+"""CUDA-graph replay of the update (RL.UpdateGraph) against the eager launches, and learn_and_update end to end
+on the GPU replay buffers (RL.py:120-143)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from cacto_b200.conf import get_conf
+
+pytestmark = pytest.mark.gpu
+
+
+def build(system='manipulator', seed=0, **over):
+    from cacto_b200 import environment as genv
+    from cacto_b200.NeuralNetwork import NN
+    from cacto_b200.RL import RL_AC
+    conf = get_conf(system, **over)
+    env = genv.make_env(conf)
+    rl = RL_AC(env, NN(env, conf, 1e-2, seed=seed), conf, 0)
+    rl.setup_model()
+    return conf, rl
+
+
+def fill(buffer, conf, n_rows, seed=0):
+    rng = np.random.default_rng(seed)
+    ns = conf.nb_state
+    lo, hi = np.asarray(conf.x_init_min, float), np.asarray(conf.x_init_max, float)
+    s = rng.uniform(lo, hi, (n_rows, ns))
+    sn = rng.uniform(lo, hi, (n_rows, ns))
+    dv = rng.normal(size=(n_rows, ns))
+    dv[:, -1] = 0
+    buffer.add((s,), (rng.uniform(-5, 0, n_rows),), (sn,), (dv,), ((rng.uniform(size=n_rows) < 0.5).astype(float),),
+               ((rng.uniform(size=n_rows) < 0.05).astype(float),))
+
+
+def weights_of(rl):
+    return [w.copy() for n in (rl.critic_model, rl.target_critic, rl.actor_model) for w in n.get_weights()]
+
+
+@pytest.mark.parametrize('lr_schedule', [0, 1])
+def test_graph_replay_equals_eager_updates(lr_schedule):
+    from cacto_b200.replay_buffer import ReplayBuffer
+    conf, rl_e = build(LR_SCHEDULE=lr_schedule)
+    _, rl_g = build(LR_SCHEDULE=lr_schedule)
+    buf = ReplayBuffer(conf)
+    fill(buf, conf, 5000)
+    before = weights_of(rl_g)
+    g = rl_g.make_update_graph()
+    for a, b in zip(before, weights_of(rl_g)):                 # capture must leave the training state untouched
+        np.testing.assert_array_equal(a, b)
+    assert rl_g.critic_optimizer.iterations == 0 and int(rl_g.critic_optimizer._dev['step'][0]) == 0
+    for it in range(4):
+        idx = np.random.default_rng(it).integers(0, 5000, conf.BATCH_SIZE)
+        batch = buf.sample(idx)
+        rtg_e, V_e, Vt_e = rl_e.update(batch[0], batch[2], batch[1], batch[3], batch[4], batch[5], batch[6], fuse_target=True)
+        buf.sample(idx, out=g.io)
+        rtg_g, V_g, Vt_g = g.replay()
+        torch.testing.assert_close(rtg_g, rtg_e, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(V_g, V_e, rtol=1e-5, atol=1e-6)
+    assert rl_g.critic_optimizer.iterations == rl_e.critic_optimizer.iterations == 4
+    assert int(rl_g.actor_optimizer._dev['step'][0]) == 4
+    for a, b in zip(weights_of(rl_e), weights_of(rl_g)):
+        assert np.abs(a - b).max() <= 2e-5 * max(np.abs(a).max(), 1e-3)
+
+
+@pytest.mark.parametrize('alpha', [0, 0.6])
+def test_learn_and_update_runs_with_both_buffers(alpha):
+    from cacto_b200.replay_buffer import PrioritizedReplayBuffer, ReplayBuffer
+    conf, rl = build(prioritized_replay_alpha=alpha, UPDATE_LOOPS=np.array([12]), save_interval=10 ** 9)
+    buf = PrioritizedReplayBuffer(conf) if alpha else ReplayBuffer(conf)
+    fill(buf, conf, 3000)
+    random.seed(0)
+    np.random.seed(0)
+    w0 = weights_of(rl)
+    cnt = rl.learn_and_update(0, buf, 0)
+    assert cnt == 12 and rl.actor_optimizer.iterations == 12
+    w1 = weights_of(rl)
+    assert all(np.isfinite(w).all() for w in w1)
+    assert any(np.abs(a - b).max() > 0 for a, b in zip(w0, w1))
+    rl.update_graph = rl.make_update_graph()
+    cnt = rl.learn_and_update(cnt, buf, 0)
+    assert cnt == 24 and rl.critic_optimizer.iterations == 24
+    assert all(np.isfinite(w).all() for w in weights_of(rl))
+    if alpha:
+        assert buf._max_priority >= 1.0 and buf.exp_counter.sum() > 0
