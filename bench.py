@@ -291,6 +291,8 @@ def run_b200(args):
     # the same update replayed as a CUDA graph (6 kernel nodes + NCCL all-reduces when world > 1)
     graph_updates_per_s = None
     try:
+        if world > 1:            # a capture failure on one rank would leave the others blocked in the all-reduce
+            raise RuntimeError('CUDA-graph replay is only benchmarked at N = 1 (eager launches are used when data-parallel)')
         ug = rl.make_update_graph(Bu)
         for k_, t_ in (('state', s), ('state_next', sn), ('partial_rtg', pr), ('dVdx', dv), ('done', d), ('term', term), ('weights', w)):
             ug.io[k_].copy_(t_)
