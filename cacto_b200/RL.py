@@ -192,7 +192,27 @@ class RL_AC:
         ICS = np.asarray(ICS, dtype=np.float64).reshape(-1, self.conf.nb_state)
         return (self.conf.NSTEPS - (ICS[:, -1] / self.conf.dt).astype(np.int64)).astype(np.int32)
 
-    def rollout_batch(self, ICS, ep, horizon=None, with_reward=False):
+    # Rollout engines: 'fma' = fp32 CUDA-core kernel (cacto_rollout), 'tc' = tcgen05 3xTF32 kernel (cacto_rollout_tc).
+    rollout_engine = 'fma'
+
+    def _launch_rollout(self, ep, ics, hz, T_max, states, controls, flags, rewards, B, engine=None):
+        engine = engine or self.rollout_engine
+        use_actor = int(ep != 0)
+        if use_actor and engine == 'tc':
+            am = self.actor_model
+            img = getattr(self, '_w2img', None)
+            if img is None:
+                img = torch.empty(int(lib.cacto_actor_tc_image_floats()), dtype=torch.float32, device=am.params.device)
+                self._w2img = img
+            check(lib.cacto_actor_tc_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc_prepare')
+            check(lib.cacto_rollout_tc(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
+                                       ptr(rewards), B, stream_ptr()), 'rollout_tc')
+        else:
+            actor = self.actor_model.params if use_actor else None
+            check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
+                                    ptr(rewards), B, stream_ptr()), 'rollout')
+
+    def rollout_batch(self, ICS, ep, horizon=None, with_reward=False, engine=None):
         """All warm-starts of RL.py:197-233 for ICS[B, ns] in one launch of the fused actor+dynamics kernel.
         Returns a dict: states [T_max+1, ns, B] and controls [T_max, na, B] (fp64, structure-of-arrays, time-major;
         ``states.permute(2, 0, 1)`` is the reference's per-rollout [T+1, ns] view), horizon [B] (NSTEPS_SH),
@@ -209,20 +229,17 @@ class RL_AC:
         controls = torch.full((T_max, c.nb_action, B), float('nan'), dtype=torch.float64, device=dev)
         flags = torch.empty(B, dtype=torch.int32, device=dev)
         rewards = torch.full((T_max + 1, B), float('nan'), dtype=torch.float64, device=dev) if with_reward else None
-        use_actor = int(ep != 0)
-        actor = self.actor_model.params if use_actor else None
-        check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
-                                ptr(rewards), B, stream_ptr()), 'rollout')
+        self._launch_rollout(ep, ics, hz, T_max, states, controls, flags, rewards, B, engine)
         out = dict(states=states, controls=controls, horizon=hz, success=flags)
         if with_reward:
             out['rewards'] = rewards
         return out
 
-    def rollout_to_host(self, ics_host, ep, states_host, controls_host, flags_host, mode='staged'):
+    def rollout_to_host(self, ics_host, ep, states_host, controls_host, flags_host, mode='zero_copy', engine=None):
         """Host-to-host rollouts for the TO feeder: ``ics_host`` [B, ns] fp64 (pinned) -> ``states_host``
         [T_max+1, ns, B], ``controls_host`` [T_max, na, B] fp64 and ``flags_host`` [B] int32 (pinned).
-        mode 'staged': H2D, kernel into HBM, D2H.  mode 'zero_copy': the kernel stores the trajectories
-        straight into the pinned host buffers over PCIe (UVA), overlapping the transfer with the compute."""
+        mode 'zero_copy' (default): the kernel stores the trajectories straight into the pinned host buffers over
+        PCIe (UVA), so the transfer overlaps the compute.  mode 'staged': H2D, kernel into HBM, D2H."""
         c = self.conf
         dev = _device()
         B = ics_host.shape[0]
@@ -230,12 +247,9 @@ class RL_AC:
         ics = ics_host.to(dev, non_blocking=True)
         hz_np = self.horizon(ics_host.numpy())
         hz = torch.as_tensor(hz_np).to(dev, non_blocking=True)
-        use_actor = int(ep != 0)
-        actor = self.actor_model.params if use_actor else None
         if mode == 'zero_copy':
             flags = torch.empty(B, dtype=torch.int32, device=dev)
-            check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(states_host), ptr(controls_host),
-                                    ptr(flags), ptr(None), B, stream_ptr()), 'rollout')
+            self._launch_rollout(ep, ics, hz, T_max, states_host, controls_host, flags, None, B, engine)
             flags_host.copy_(flags, non_blocking=True)
         else:
             buf = getattr(self, '_host_stage', None)
@@ -244,8 +258,7 @@ class RL_AC:
                        torch.empty((T_max, c.nb_action, B), dtype=torch.float64, device=dev),
                        torch.empty(B, dtype=torch.int32, device=dev))
                 self._host_stage = buf
-            check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(buf[0]), ptr(buf[1]), ptr(buf[2]),
-                                    ptr(None), B, stream_ptr()), 'rollout')
+            self._launch_rollout(ep, ics, hz, T_max, buf[0], buf[1], buf[2], None, B, engine)
             states_host.copy_(buf[0], non_blocking=True)
             controls_host.copy_(buf[1], non_blocking=True)
             flags_host.copy_(buf[2], non_blocking=True)

@@ -116,6 +116,16 @@ int cacto_rollout(const cacto_sys_params* p, const float* actor_params, int use_
                   const int32_t* horizon, int32_t T_max, double* states, double* controls, int32_t* flags,
                   double* rewards, int64_t B, void* stream);
 
+/* ---- K1 on tcgen05 tensor cores: same contract as cacto_rollout (use_actor = 1), with the 256x256 hidden layer
+ *      computed by tcgen05.mma kind::tf32 with 3xTF32 operand splitting (fp32-class accuracy, accumulators in TMEM).
+ *      w2img (cacto_actor_tc_image_floats() floats, 128-byte aligned, caller-owned) is the hi/lo-split, UMMA-laid-out
+ *      image of the actor's W2 built by cacto_actor_tc_prepare; rebuild it whenever the actor changes. */
+int64_t cacto_actor_tc_image_floats(void);
+int cacto_actor_tc_prepare(const float* actor_params, int32_t ns, int32_t na, float* w2img, void* stream);
+int cacto_rollout_tc(const cacto_sys_params* p, const float* actor_params, const float* w2img, const double* ics,
+                     const int32_t* horizon, int32_t T_max, double* states, double* controls, int32_t* flags,
+                     double* rewards, int64_t B, void* stream);
+
 /* ---- N4: NN.eval over a batch (NeuralNetwork.py:130-138): out[B][na] (actor) / out[B][1] (critic) */
 int cacto_actor_forward(const cacto_sys_params* p, const float* actor_params, const float* state, float* out,
                         int64_t B, void* stream);
