@@ -2,17 +2,17 @@
 """bench.py -- CACTO hot-path throughput on B200 (BASELINE.json metric: manipulator rollout env-steps/s
 + Sobolev actor-critic updates/s).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--engine tc|fma]
 
 One "step" = one pass of the fused rollout kernel (K1) over this rank's batch of synthetic initial
 conditions: BASELINE config[3] (3-DOF planar manipulator, 1 M rollouts x 100 steps sharded over 8 GPUs)
 = 131072 rollouts x 100 env-steps per GPU (weak scaling: per-GPU work fixed).  `value` counts env-steps
-with the inputs resident in HBM; `e2e` runs the same pass through the public Python API with the initial
-conditions in pinned HOST memory and the warm-start trajectories copied back to pinned host memory inside
-the timed region.  The secondary number (Sobolev critic+actor updates/s, conf batch 64 per GPU) is in
-`extra`.  `cpu_baseline` times the oracle's restatement of the reference's rollout loop
-(RL.py:221-231 over multiprocessing.Pool like main.py:220-225) on the host cores, on a bounded sample.
-`--impl reference` prints that CPU arm alone as the reference line.
+with the inputs resident in HBM; `e2e` runs the same pass through the public Python API
+(RL_AC.rollout_to_host) with the initial conditions in pinned HOST memory and the fp64 warm-start
+trajectories delivered to pinned host memory inside the timed region.  The secondary number (Sobolev
+critic+actor updates/s, conf batch 64 per GPU) is in `extra`.  `cpu_baseline` times the oracle's restatement
+of the reference's rollout loop (RL.py:221-231 over multiprocessing.Pool like main.py:220-225) on the host
+cores, on a bounded sample.  `--impl reference` prints that CPU arm alone as the reference line.
 """
 import argparse
 import json
@@ -82,14 +82,13 @@ def run_reference(args):
     per_core = 6
     for _ in range(args.warmup):
         cpu_rollout_rate(cores, 1)
-    t_all = time.perf_counter()
     for _ in range(args.steps):
-        rate, steps, dt = cpu_rollout_rate(cores, per_core)
-        vals.append((rate, steps, dt))
+        vals.append(cpu_rollout_rate(cores, per_core))
     total_steps = sum(v[1] for v in vals)
     total_dt = sum(v[2] for v in vals)
     rate = total_steps / total_dt
-    sample = f'{cores * per_core} rollouts x 100 steps per bench step ({total_steps} env-steps in {total_dt:.1f} s), t0 = 0'
+    sample = (f'{cores * per_core} rollouts x 100 steps per bench step ({total_steps} env-steps in {total_dt:.1f} s), t0 = 0; oracle port '
+              f'(B=1 torch-CPU actor forward + NumPy fp64 RNEA dynamics per step) over multiprocessing.Pool({cores})')
     print(json.dumps({
         'impl': 'reference', 'metric': 'manipulator rollout env-steps/s', 'value': rate, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_dt / max(1, args.steps), 'higher_is_better': True,
@@ -123,10 +122,10 @@ class ClockSampler:
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
                     if v.lower().startswith('active'):
                         reasons.add(name)
@@ -134,7 +133,8 @@ class ClockSampler:
                 pass
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm),
+                'power_w_max': float(max(pw))}
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -151,7 +151,8 @@ def run_b200(args):
         rate, steps, dt = cpu_rollout_rate(cores, per_core)
         cpu = {'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
                'sample': f'{cores * per_core} rollouts x 100 steps ({steps} env-steps, {dt:.1f} s): oracle restatement of RL.py:221-231 '
-                         f'(B=1 torch-CPU actor forward + NumPy fp64 dynamics per step) over multiprocessing.Pool({cores})'}
+                         f'(B=1 torch-CPU actor forward + NumPy fp64 RNEA dynamics per step; slower than Pinocchio C++ would be) over '
+                         f'multiprocessing.Pool({cores})'}
 
     import torch
     import torch.distributed as dist
@@ -169,6 +170,7 @@ def run_b200(args):
     env = genv.make_env(conf)
     rl = RL_AC(env, NN(env, conf, 1e-2, seed=0), conf, 0, dist=dist if world > 1 else None)
     rl.setup_model()
+    rl.rollout_engine = args.engine
     B, T, ns, na = args.rollouts_per_gpu, conf.NSTEPS, conf.nb_state, conf.nb_action
     rng = np.random.default_rng(1000 + rank)
     X0 = rng.uniform(conf.x_init_min, conf.x_init_max, (B, ns))
@@ -181,12 +183,11 @@ def run_b200(args):
     flags = torch.empty(B, dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MiB > 126 MB L2
     stream = torch.cuda.current_stream()
-    P = env._p
-    lib, ptr, check = _lib.lib, _lib.ptr, _lib.check
+    lib, ptr = _lib.lib, _lib.ptr
 
-    def rollout_step():
-        check(lib.cacto_rollout(P, ptr(rl.actor_model.params), 1, ptr(ics), ptr(hz), T, ptr(states), ptr(controls), ptr(flags), ptr(None),
-                                B, _lib.stream_ptr()), 'rollout')
+    def rollout_step():      # the launches of RL_AC.rollout_batch on pre-allocated outputs (tc: W2 image refresh + rollout kernel)
+        rl._launch_rollout(1, ics, hz, T, states, controls, flags, None, B)
+    launches_per_step = 2 if args.engine == 'tc' else 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -195,7 +196,7 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     def timed(fn, steps, do_flush=True):
-        """Sum of per-step CUDA-event durations (ms) on the launching stream; L2 flushed between steps."""
+        """Per-step CUDA-event durations (ms) on the launching stream; L2 flushed between steps."""
         evs = []
         for _ in range(steps):
             if do_flush:
@@ -206,7 +207,14 @@ def run_b200(args):
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
-    # FP32 FMA peak, measured in-run (roofline denominator of the fp32-FMA rollout kernel)
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # FP32 FMA peak, measured in-run (roofline denominator of the fp32-FMA kernels)
     pk_out = torch.zeros(4, dtype=torch.float32, device=dev)
     pk_iters, pk_blocks = 4096, 148 * 16
     for _ in range(2):
@@ -223,39 +231,27 @@ def run_b200(args):
         sampler.start()
     ms = timed(rollout_step, K)
     barrier()
-    total_ms = float(sum(ms))
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t[0])
+    total_ms = max_over_ranks(float(sum(ms)))
     assert bool(flags.all()), 'a rollout hit NaN'
-    env_steps = B * T * K * world
-    value = env_steps / (total_ms * 1e-3)
+    value = B * T * K * world / (total_ms * 1e-3)
     kernel_ms = float(np.mean(ms))
     achieved_tflops = B * T * FLOPS_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e12
 
-    # ---- e2e: host ICS (pinned) -> H2D -> rollout -> D2H of the warm-start trajectories (pinned)
+    # ---- e2e: host ICS (pinned) -> H2D -> rollout -> fp64 warm-start trajectories in pinned host memory
     st_host = torch.empty((T + 1, ns, B), dtype=torch.float64).pin_memory()
     ct_host = torch.empty((T, na, B), dtype=torch.float64).pin_memory()
     fl_host = torch.empty(B, dtype=torch.int32).pin_memory()
-
-    def e2e_step():
-        out = rl.rollout_to_host(ics_host, 1, st_host, ct_host, fl_host)
-        return out
     for _ in range(max(1, W // 2)):
-        e2e_step()
+        rl.rollout_to_host(ics_host, 1, st_host, ct_host, fl_host)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        e2e_step()
+        rl.rollout_to_host(ics_host, 1, st_host, ct_host, fl_host)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert bool(fl_host.all())
     e2e_value = B * T * K * world / e2e_s
-    h2d = ics_host.numel() * 8
+    h2d = ics_host.numel() * 8 + B * 4
     d2h = (st_host.numel() + ct_host.numel()) * 8 + fl_host.numel() * 4
 
     # ---- K3 updates/s (secondary metric): conf batch per GPU, data resident, gradients all-reduced over NCCL
@@ -282,38 +278,27 @@ def run_b200(args):
         update_step()
     b.record(stream)
     torch.cuda.synchronize()
-    up_ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([up_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        up_ms = float(t[0])
-    updates_per_s = n_up / (up_ms * 1e-3)
-    # the same update replayed as a CUDA graph (6 kernel nodes + NCCL all-reduces when world > 1)
+    updates_per_s = n_up / (max_over_ranks(a.elapsed_time(b)) * 1e-3)
+    # the same update replayed as a CUDA graph (6 kernel nodes)
     graph_updates_per_s = None
-    try:
-        if world > 1:            # a capture failure on one rank would leave the others blocked in the all-reduce
-            raise RuntimeError('CUDA-graph replay is only benchmarked at N = 1 (eager launches are used when data-parallel)')
-        ug = rl.make_update_graph(Bu)
-        for k_, t_ in (('state', s), ('state_next', sn), ('partial_rtg', pr), ('dVdx', dv), ('done', d), ('term', term), ('weights', w)):
-            ug.io[k_].copy_(t_)
-        for _ in range(20):
-            ug.replay()
-        barrier()
-        n_gr = 1000
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for _ in range(n_gr):
-            ug.replay()
-        b.record(stream)
-        torch.cuda.synchronize()
-        gr_ms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([gr_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            gr_ms = float(t[0])
-        graph_updates_per_s = n_gr / (gr_ms * 1e-3)
-    except Exception as exc:           # report, do not hide
-        graph_updates_per_s = f'failed: {type(exc).__name__}: {exc}'
+    if world == 1:               # a capture failure on one rank would leave the others blocked in the all-reduce
+        try:
+            ug = rl.make_update_graph(Bu)
+            for k_, t_ in (('state', s), ('state_next', sn), ('partial_rtg', pr), ('dVdx', dv), ('done', d), ('term', term), ('weights', w)):
+                ug.io[k_].copy_(t_)
+            for _ in range(20):
+                ug.replay()
+            torch.cuda.synchronize()
+            n_gr = 1000
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(n_gr):
+                ug.replay()
+            b.record(stream)
+            torch.cuda.synchronize()
+            graph_updates_per_s = n_gr / (a.elapsed_time(b) * 1e-3)
+        except Exception as exc:           # report, do not hide
+            graph_updates_per_s = f'failed: {type(exc).__name__}: {exc}'
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -322,25 +307,39 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
+        bf16 = peaks.get('bf16_tflops') or 1590.0
+        peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks.get('bf16_tflops') else 'fallback 1590 TFLOP/s'
+        if args.engine == 'tc':
+            roof = {'bound': 'tensor', 'achieved': achieved_tflops, 'peak': bf16, 'unit': 'TFLOP/s', 'frac': achieved_tflops / bf16,
+                    'traffic': None, 'peak_source': peak_src,
+                    'ceiling_3xtf32': bf16 / 6.0, 'frac_of_3xtf32_ceiling': achieved_tflops / (bf16 / 6.0),
+                    'note': 'k_rollout_tc: 256x256 actor layer on tcgen05.mma kind::tf32 with 3xTF32 operand splitting (fp32-class accuracy: parity '
+                            'gate 1e-5). achieved counts ALGORITHMIC flops (2 P_a + F_dyn per env-step); the tensor pipe executes 3 tf32 UMMAs per '
+                            'logical product and tf32 runs at half the bf16 rate, so the reachable ceiling is peak/6.',
+                    'flops_per_env_step': FLOPS_PER_ENV_STEP, 'kernel_ms': kernel_ms}
+        else:
+            roof = {'bound': 'fp32_fma', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
+                    'frac': achieved_tflops / fma_peak_tflops, 'traffic': None, 'peak_source': 'cacto_peak_fma_fp32 measured in this run',
+                    'frac_of_bf16_tensor_peak': achieved_tflops / bf16,
+                    'note': 'k_rollout: fp32 CUDA-core FMA contraction', 'flops_per_env_step': FLOPS_PER_ENV_STEP, 'kernel_ms': kernel_ms}
         line = {
             'metric': 'manipulator rollout env-steps/s', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32 actor MLP / f64 dynamics', 'data': 'synthetic',
+            'dtype': 'f32 actor MLP (3xTF32 tensor cores) / f64 dynamics' if args.engine == 'tc' else 'f32 actor MLP / f64 dynamics',
+            'data': 'synthetic',
             'config': {'workload': 'BASELINE config[3]: 3-DOF planar manipulator policy rollouts (create_TO_init), '
                                    f'{B} rollouts x {T} steps per GPU (1 M over 8 GPUs), seeded-init actor {ns}->256->256->{na}',
-                       'rollouts_per_gpu': B, 'horizon': T, 'l2': 'flushed between timed steps (256 MiB write); outputs 1.06 GB/step',
+                       'rollouts_per_gpu': B, 'horizon': T, 'engine': args.engine,
+                       'l2': 'flushed between timed steps (256 MiB write); outputs 1.06 GB/step',
                        'parallelism': f'dp{world} over independent rollouts, no collective on the rollout path'},
-            'roofline': {'bound': 'fp32_fma', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
-                         'frac': achieved_tflops / fma_peak_tflops, 'traffic': None,
-                         'note': 'k_rollout is an fp32 CUDA-core FMA contraction (parity gate 1e-5 rules out bf16/tf32 UMMA); peak = FP32 FMA '
-                                 'rate measured in this run (cacto_peak_fma_fp32). Against the measured bf16 tensor peak '
-                                 f"({peaks.get('bf16_tflops')} TFLOP/s) the fraction is {achieved_tflops / peaks['bf16_tflops'] if peaks.get('bf16_tflops') else None}",
-                         'flops_per_env_step': FLOPS_PER_ENV_STEP, 'kernel_ms': kernel_ms},
-            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': K,
+            'roofline': roof,
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'note': 'RL_AC.rollout_to_host: kernel stores the fp64 trajectories straight into pinned host memory (zero-copy over PCIe)'},
+            'gpu_launches': K * launches_per_step,
             'clocks': clocks,
-            'extra': {'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s, 'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world,
-                      'update_launches_per_update': 4, 'fp32_fma_peak_tflops_measured': fma_peak_tflops},
+            'extra': {'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s,
+                      'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world, 'update_kernels_per_update': 6,
+                      'fp32_fma_peak_tflops_measured': fma_peak_tflops},
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu
@@ -355,6 +354,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--engine', default='tc', choices=['tc', 'fma'])
     ap.add_argument('--rollouts-per-gpu', type=int, default=ROLLOUTS_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

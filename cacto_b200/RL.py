@@ -193,7 +193,7 @@ class RL_AC:
         return (self.conf.NSTEPS - (ICS[:, -1] / self.conf.dt).astype(np.int64)).astype(np.int32)
 
     # Rollout engines: 'fma' = fp32 CUDA-core kernel (cacto_rollout), 'tc' = tcgen05 3xTF32 kernel (cacto_rollout_tc).
-    rollout_engine = 'fma'
+    rollout_engine = 'tc'
 
     def _launch_rollout(self, ep, ics, hz, T_max, states, controls, flags, rewards, B, engine=None):
         engine = engine or self.rollout_engine

@@ -32,10 +32,12 @@ def ics(conf, B, seed):
 
 
 @pytest.mark.parametrize('system', SYSTEM_IDS)
-@pytest.mark.parametrize('ep', [0, 1])
-def test_rollout_batch_matches_oracle(system, ep):
+@pytest.mark.parametrize('ep,engine', [(0, 'fma'), (1, 'fma'), (1, 'tc')])
+def test_rollout_batch_matches_oracle(system, ep, engine):
+    """engine 'fma' = fp32 CUDA-core kernel, 'tc' = tcgen05 3xTF32 kernel (256 rollouts per CTA)."""
     conf, env, rl = setup(system)
-    B = 70 if system != 'ur5' else 5          # 70: two CTAs, ragged tile, mixed horizons
+    rl.rollout_engine = engine
+    B = (70 if engine == 'fma' else 300) if system != 'ur5' else 5      # more than one CTA, ragged tile, mixed horizons
     X0 = ics(conf, B, 3)
     X0[0, -1] = 0.0                            # full horizon
     X0[1, -1] = (conf.NSTEPS - 1) * conf.dt    # one step
@@ -50,8 +52,9 @@ def test_rollout_batch_matches_oracle(system, ep):
     def actor_eval(x):
         with torch.no_grad():
             return onn.actor_forward(ap, torch.tensor(x, dtype=torch.float32), conf).numpy()[0]
-    n_check = B if system != 'ur5' else 3
-    for b in range(n_check):
+    n_check = (B if system != 'ur5' else 3) if engine == 'fma' else min(B, 12)
+    check = list(range(n_check)) if engine == 'fma' else [i for i in ([0, 1, 127, 128, 255, 256, B - 1] + list(range(2, 7))) if i < B][:n_check]
+    for b in check:
         _, st, ct, T, ok = ortg.create_to_init(conf, oenv, actor_eval, ep, X0[b])
         assert ok == 1 and T == hz[b] == ortg.horizon(conf, X0[b, -1])
         sc = np.abs(st).max(axis=0) + 1e-12
@@ -79,8 +82,24 @@ def test_create_TO_init_matches_reference_goldens(system):
             assert np.abs(ct - ref_c).max() <= tol * max(1.0, np.abs(ref_c).max())
 
 
-def test_horizon_zero_and_nan_flag():
+def test_tensor_core_engine_agrees_with_fma_engine():
+    """Full-size tile coverage: 1000 manipulator rollouts with mixed horizons, both engines, same actor."""
     conf, env, rl = setup('manipulator')
+    X0 = ics(conf, 1000, 7)
+    a = rl.rollout_batch(X0, 1, engine='fma')
+    b = rl.rollout_batch(X0, 1, engine='tc')
+    assert bool((torch.isnan(a['states']) == torch.isnan(b['states'])).all())
+    m = ~torch.isnan(a['states'])
+    assert float((a['states'][m] - b['states'][m]).abs().max()) < 1e-5
+    m = ~torch.isnan(a['controls'])
+    assert float((a['controls'][m] - b['controls'][m]).abs().max()) < 1e-5
+    assert bool((a['success'] == b['success']).all())
+
+
+@pytest.mark.parametrize('engine', ['fma', 'tc'])
+def test_horizon_zero_and_nan_flag(engine):
+    conf, env, rl = setup('manipulator')
+    rl.rollout_engine = engine
     x0 = ics(conf, 4, 1)
     x0[0, -1] = conf.NSTEPS * conf.dt          # NSTEPS_SH = 0 (RL.py:202-203)
     assert rl.create_TO_init(1, x0[0])[-1] == 0
