@@ -22,11 +22,14 @@
 namespace cacto {
 
 constexpr int TC_TILE = 128;                 // rollouts per UMMA tile (M)
-constexpr int TC_TILES = 2;                  // tiles per CTA
+constexpr int TC_TILES = 2;                  // tiles per CTA.  Measured: 2 tiles x KC 32, 1 CTA/SM = 7.9 ms; 1 tile x KC 16, 2 CTAs/SM = 10.2 ms
+constexpr int TC_CTAS_PER_SM = TC_TILES == 1 ? 2 : 1;
 constexpr int TC_ROLLOUTS = TC_TILE * TC_TILES;
 constexpr int TC_WORKERS = TC_ROLLOUTS;      // worker threads
 constexpr int TC_THREADS = TC_WORKERS + 64;  // + MMA warp + TMA warp
-constexpr int TC_KC = 32;                    // hidden units per K-chunk
+constexpr int TC_MMA_WARP = TC_WORKERS / 32;
+constexpr int TC_TMEM_COLS = TC_TILES * ACTOR_H;
+constexpr int TC_KC = TC_TILES == 1 ? 16 : 32;   // hidden units per K-chunk (sized so that the CTA's shared memory allows TC_CTAS_PER_SM)
 constexpr int TC_NCHUNK = ACTOR_H / TC_KC;   // 8
 constexpr int TC_A_IMG = TC_TILE * TC_KC;    // floats of one A image (hi or lo) of a chunk: 4096 (16 KB)
 constexpr int TC_B_IMG = ACTOR_H * TC_KC;    // floats of one W2 image (hi or lo) of a chunk: 8192 (32 KB)
@@ -109,11 +112,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
 }
 
 template <int SYS>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_rollout_tc(const __grid_constant__ cacto_sys_params P, const float* __restrict__ actor,
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM) k_rollout_tc(const __grid_constant__ cacto_sys_params P, const float* __restrict__ actor,
                                                               const float* __restrict__ w2img, const double* __restrict__ ics,
                                                               const int32_t* __restrict__ horizon, int T_max, double* __restrict__ states,
                                                               double* __restrict__ controls, int32_t* __restrict__ flags,
-                                                              double* __restrict__ rewards, int64_t B) {
+                                                              double* __restrict__ rewards, int64_t B, int num_sms) {
   constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA, NS = NX + 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -139,8 +142,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rollout_tc(const __grid_const
     for (int m = 0; m < TC_TILES; ++m) { mbar_init(&sm.a_full[m], TC_TILE); mbar_init(&sm.a_empty[m], 1); mbar_init(&sm.d_full[m], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
+  if (warp == TC_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(TC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   __syncthreads();
@@ -161,6 +164,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rollout_tc(const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int tmax = sm.tmax;
   const uint32_t tmem = sm.tmem_base;
+  if (TC_CTAS_PER_SM == 2 && ((blockIdx.x / (unsigned)num_sms) & 1u)) {
+    // CTAs i and i + num_sms share an SM in the first wave: start the second one about half a step later so that the
+    // MMAs of one CTA fill the epilogue / dynamics bubble of the other (later waves are staggered by completion order).
+    const long long t0 = clock64();
+    while (clock64() - t0 < 9000) {}
+  }
 
   if (worker) {
     // =================================================================== workers
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rollout_tc(const __grid_const
       }
     }
     if (owner) flags[b] = ok;
-  } else if (warp == 8) {
+  } else if (warp == TC_MMA_WARP) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ACTOR_H >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
@@ -300,18 +309,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_rollout_tc(const __grid_const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (warp == TC_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
 }
 
 template <int SYS>
 static int launch_rollout_tc(const cacto_sys_params& P, const float* actor, const float* w2img, const double* ics, const int32_t* horizon,
                              int T_max, double* states, double* controls, int32_t* flags, double* rewards, int64_t B, cudaStream_t st) {
   auto k = k_rollout_tc<SYS>;
-  const size_t sm = sizeof(TcSmem) + 1024;
+  const size_t sm = sizeof(TcSmem);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   k<<<(unsigned)((B + TC_ROLLOUTS - 1) / TC_ROLLOUTS), TC_THREADS, sm, st>>>(P, actor, w2img, ics, horizon, T_max, states, controls, flags,
-                                                                              rewards, B);
+                                                                              rewards, B, num_sms);
   CACTO_LAUNCH_CHECK();
   return 0;
 }
