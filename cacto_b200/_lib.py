@@ -11,7 +11,7 @@ import numpy as np
 from . import robots
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcacto_b200.so')
+LIB_PATH = os.environ.get('CACTO_B200_LIB', os.path.join(_HERE, 'libcacto_b200.so'))   # override: instrumented builds
 
 SYSTEM_CODE = dict(single_integrator=0, double_integrator=1, car=2, car_park=3, manipulator=4, ur5=5)
 MAX_NS, MAX_NA, MAX_JOINTS = 13, 6, 6

@@ -37,7 +37,7 @@ __device__ __forceinline__ void fma4(float4& acc, float a, const float4& w) {
   acc.w = fmaf(a, w.w, acc.w);
 }
 
-// C = A * W.  A: shared [S][lda]; W: global, row k at W + k*ldw (ldw % 4 == 0, 16-byte aligned).
+// C = A * W.  A: shared [S][lda]; W: global or shared, row k at W + k*ldw (ldw % 4 == 0, 16-byte aligned).
 // epi(row, col, acc4) is called once per (row, 4-column group) owned by the thread.
 // The caller synchronises (A must be complete before the call; the epilogue may overwrite A only
 // after a __syncthreads() placed by the caller -- see the `sync_before_epilogue` flag).
@@ -59,12 +59,12 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
     float4 w[4], wn[4];
     if (K4 > 0) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(wp + (size_t)kk * ldw4);
+      for (int kk = 0; kk < 4; ++kk) w[kk] = wp[(size_t)kk * ldw4];
     }
     for (int k = 0; k < K4; k += 4) {
       if (k + 4 < K4) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) wn[kk] = __ldg(wp + (size_t)(k + 4 + kk) * ldw4);
+        for (int kk = 0; kk < 4; ++kk) wn[kk] = wp[(size_t)(k + 4 + kk) * ldw4];
       }
 #pragma unroll
       for (int r = 0; r < TM; ++r) {
@@ -78,7 +78,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
       for (int kk = 0; kk < 4; ++kk) w[kk] = wn[kk];
     }
     for (int k = K4; k < K; ++k) {
-      const float4 wk = __ldg(wp + (size_t)k * ldw4);
+      const float4 wk = wp[(size_t)k * ldw4];
 #pragma unroll
       for (int r = 0; r < TM; ++r) fma4(acc[r], a0[r * lda + k], wk);
     }
@@ -219,7 +219,7 @@ __device__ __forceinline__ void tile_gemm_small(const float* __restrict__ A, int
     float acc = 0.f;
     if (valid) {
       for (int k = sub; k < K; k += G) {
-        const float w = W_KN ? __ldg(W + (size_t)k * N + j) : __ldg(W + (size_t)j * ldw + k);
+        const float w = W_KN ? W[(size_t)k * N + j] : W[(size_t)j * ldw + k];
         acc = fmaf(A[s * lda + k], w, acc);
       }
     }

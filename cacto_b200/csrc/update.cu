@@ -75,32 +75,75 @@ __device__ __forceinline__ void seq_push_critic_bwd(WeightSeq& q, const CriticLa
   seq_push<CR_H1>(q, wT + L.W[1], CR_H2);
 }
 
+// Small parameters of a critic (first layer, all biases, output weights) copied once per kernel into shared memory:
+// they are touched by every phase of the sweeps, and an L2 round trip per phase is what a latency-bound kernel cannot hide.
+struct CriticSmall {
+  alignas(16) float W1[CACTO_MAX_NS * CR_H1];
+  alignas(16) float b[CW + 4];          // hidden biases at koff(l), output bias at CW
+  alignas(16) float w5[CR_H4];
+};
+struct CriticPtrs {
+  const float* W0;
+  const float* b[5];
+  const float* W4;
+};
+__device__ __forceinline__ void load_critic_small(CriticSmall& d, const float* __restrict__ w, const CriticLayout& L) {
+  for (int i = threadIdx.x; i < L.ns * CR_H1; i += UP_NT) d.W1[i] = w[L.W[0] + i];
+  for (int i = threadIdx.x; i < CW; i += UP_NT) {
+    const int l = i < CR_H1 ? 0 : (i < CR_H1 + CR_H2 ? 1 : (i < CR_H1 + CR_H2 + CR_H3 ? 2 : 3));
+    d.b[i] = w[L.b[l] + (i - koff(l))];
+  }
+  for (int i = threadIdx.x; i < CR_H4; i += UP_NT) d.w5[i] = w[L.W[4] + i];
+  if (threadIdx.x == 0) d.b[CW] = w[L.b[4]];
+}
+__device__ __forceinline__ CriticPtrs critic_ptrs(const CriticSmall& d) {
+  CriticPtrs p;
+  p.W0 = d.W1;
+  for (int l = 0; l < 4; ++l) p.b[l] = d.b + koff(l);
+  p.b[4] = d.b + CW;
+  p.W4 = d.w5;
+  return p;
+}
+struct ActorSmall {
+  alignas(16) float W1[CACTO_MAX_NS * ACTOR_H];
+  alignas(16) float b1[ACTOR_H];
+  alignas(16) float b2[ACTOR_H];
+  alignas(16) float W3[ACTOR_H * CACTO_MAX_NA];
+  float b3[8];
+};
+__device__ __forceinline__ void load_actor_small(ActorSmall& d, const float* __restrict__ w, const ActorLayout& L) {
+  for (int i = threadIdx.x; i < L.ns * ACTOR_H; i += UP_NT) d.W1[i] = w[L.W1 + i];
+  for (int i = threadIdx.x; i < ACTOR_H; i += UP_NT) { d.b1[i] = w[L.b1 + i]; d.b2[i] = w[L.b2 + i]; }
+  for (int i = threadIdx.x; i < ACTOR_H * L.na; i += UP_NT) d.W3[i] = w[L.W3 + i];
+  if (threadIdx.x < L.na) d.b3[threadIdx.x] = w[L.b3 + threadIdx.x];
+}
+
 // Forward pass of the sine critic for a tile, activations ping-ponging between two [S][ld] scratch
 // buffers (>= 128 columns used).  V[s] receives the value.  Ends with a __syncthreads().
 template <int S, typename SM>
-__device__ __forceinline__ void critic_forward_tile(WeightPipe& pipe, SM& sm, int& gi, const float* __restrict__ cw, const CriticLayout& L,
+__device__ __forceinline__ void critic_forward_tile(WeightPipe& pipe, SM& sm, int& gi, const CriticPtrs& cp, const CriticLayout& L,
                                                     const float (*XN)[NSP], float* bufA, float* bufB, int ld, float* V) {
-  tile_gemm<S, CR_H1, UP_NT, false>(&XN[0][0], NSP, L.ns, cw + L.W[0], CR_H1, [&](int r, int c, const float4& a) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[0] + c));
+  tile_gemm<S, CR_H1, UP_NT, false>(&XN[0][0], NSP, L.ns, cp.W0, CR_H1, [&](int r, int c, const float4& a) {
+    const float4 b = *reinterpret_cast<const float4*>(cp.b[0] + c);
     *reinterpret_cast<float4*>(bufA + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
   });
   __syncthreads();
   streamed<S, CR_H2>(pipe, sm, gi, bufA, ld, CR_H1, [&](int r, int c, const float4& a) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[1] + c));
+    const float4 b = *reinterpret_cast<const float4*>(cp.b[1] + c);
     *reinterpret_cast<float4*>(bufB + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
   });
   __syncthreads();
   streamed<S, CR_H3>(pipe, sm, gi, bufB, ld, CR_H2, [&](int r, int c, const float4& a) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[2] + c));
+    const float4 b = *reinterpret_cast<const float4*>(cp.b[2] + c);
     *reinterpret_cast<float4*>(bufA + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
   });
   __syncthreads();
   streamed<S, CR_H4>(pipe, sm, gi, bufA, ld, CR_H3, [&](int r, int c, const float4& a) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[3] + c));
+    const float4 b = *reinterpret_cast<const float4*>(cp.b[3] + c);
     *reinterpret_cast<float4*>(bufB + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
   });
   __syncthreads();
-  tile_gemm_small<S, UP_NT, 8, true>(bufB, ld, CR_H4, cw + L.W[4], 1, 0, [&](int s, int, float v) { V[s] = v + __ldg(cw + L.b[4]); });
+  tile_gemm_small<S, UP_NT, 8, true>(bufB, ld, CR_H4, cp.W4, 1, 0, [&](int s, int, float v) { V[s] = v + cp.b[4][0]; });
   __syncthreads();
 }
 
@@ -110,10 +153,11 @@ struct CriticSmem {
   alignas(128) float WB[2 * W_CHUNK];
   uint64_t bar[2];
   WeightSeq seq;
-  alignas(16) float XN[S][NSP];
-  float XNN[S][NSP], A0[S][NSP], G0[S][NSP];
+  CriticSmall sc, st;                       // critic / target critic small parameters
+  alignas(16) float X2[2 * S][NSP];         // rows [0, S): normalised state, rows [S, 2S): normalised next state
+  float A0[S][NSP], G0[S][NSP];
   float SN[S][CW], CS[S][CW], G[S][CW], DL[S][CW], A[S][CW];
-  float V[S], VT[S], VTN[S], Y[S], VBAR[S], WGT[S];
+  float V[S], VT2[2 * S], Y[S], VBAR[S], WGT[S];
   float loss;
 };
 
@@ -137,8 +181,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   int gi = 0;
   if (tid == 0) {
     sm.seq.n = 0;
-    if (!mc) seq_push_critic_fwd(sm.seq, L, tw);
-    seq_push_critic_fwd(sm.seq, L, tw);
+    seq_push_critic_fwd(sm.seq, L, tw);      // one target pass over [s; s_next] (2S rows)
     seq_push_critic_fwd(sm.seq, L, cw);
     if (sobolev) {
       seq_push_critic_bwd(sm.seq, L, cwT);
@@ -149,21 +192,26 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   }
   pipe.init(sm.WB, sm.bar);
   pipe.issue(sm.seq.ptr[0], sm.seq.first[0]);
-  load_normalised<S>(P, state, row0, rows, sm.XN);
-  if (!mc) load_normalised<S>(P, state_next, row0, rows, sm.XNN);
+  float (*XN)[NSP] = sm.X2;
+  load_normalised<S>(P, state, row0, rows, XN);
+  if (!mc) load_normalised<S>(P, state_next, row0, rows, sm.X2 + S);
+  load_critic_small(sm.sc, cw, L);
+  load_critic_small(sm.st, tw, L);
+  const CriticPtrs cp = critic_ptrs(sm.sc), tp = critic_ptrs(sm.st);
   __syncthreads();
 
   // ---- target critic: V_t(s_next) for the TD(n) tail (NeuralNetwork.py:157-158) and V_t(s) (:178)
-  if (!mc) critic_forward_tile<S>(pipe, sm, gi, tw, L, sm.XNN, &sm.A[0][0], &sm.DL[0][0], CW, sm.VTN);
-  critic_forward_tile<S>(pipe, sm, gi, tw, L, sm.XN, &sm.A[0][0], &sm.DL[0][0], CW, sm.VT);
+  // (A and DL, unused until the sweeps, serve as [2S][128] scratch)
+  if (!mc) critic_forward_tile<2 * S>(pipe, sm, gi, tp, L, sm.X2, &sm.A[0][0], &sm.DL[0][0], CR_H4, sm.VT2);
+  else critic_forward_tile<S>(pipe, sm, gi, tp, L, sm.X2, &sm.A[0][0], &sm.DL[0][0], CR_H4, sm.VT2);
   if (tid < S) {
     float y = 0.f, w = 0.f;
     if (tid < rows) {
       const int64_t b = row0 + tid;
-      y = mc ? prtg[b] : prtg[b] + (1.f - done[b]) * sm.VTN[tid];
+      y = mc ? prtg[b] : prtg[b] + (1.f - done[b]) * sm.VT2[S + tid];
       w = weights[b];
       rtg_out[b] = y;
-      Vt_out[b] = sm.VT[tid];
+      Vt_out[b] = sm.VT2[tid];
     }
     sm.Y[tid] = y;
     sm.WGT[tid] = w;
@@ -172,7 +220,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   // ---- F: forward, keeping sin z_l and cos z_l of every hidden layer
   auto f_epi = [&](int l) {
     return [&, l](int r, int c, const float4& a) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[l] + c));
+      const float4 b = *reinterpret_cast<const float4*>(cp.b[l] + c);
       float4 s, co;
       sincosf(a.x + b.x, &s.x, &co.x);
       sincosf(a.y + b.y, &s.y, &co.y);
@@ -182,7 +230,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
       *reinterpret_cast<float4*>(&sm.CS[r][koff(l) + c]) = co;
     };
   };
-  tile_gemm<S, CR_H1, UP_NT, false>(&sm.XN[0][0], NSP, ns, cw + L.W[0], CR_H1, f_epi(0));
+  tile_gemm<S, CR_H1, UP_NT, false>(&XN[0][0], NSP, ns, cp.W0, CR_H1, f_epi(0));
   __syncthreads();
   streamed<S, CR_H2>(pipe, sm, gi, &sm.SN[0][koff(0)], CW, CR_H1, f_epi(1));
   __syncthreads();
@@ -190,8 +238,8 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   __syncthreads();
   streamed<S, CR_H4>(pipe, sm, gi, &sm.SN[0][koff(2)], CW, CR_H3, f_epi(3));
   __syncthreads();
-  tile_gemm_small<S, UP_NT, 8, true>(&sm.SN[0][koff(3)], CW, CR_H4, cw + L.W[4], 1, 0,
-                                     [&](int s, int, float v) { sm.V[s] = v + __ldg(cw + L.b[4]); });
+  tile_gemm_small<S, UP_NT, 8, true>(&sm.SN[0][koff(3)], CW, CR_H4, cp.W4, 1, 0,
+                                     [&](int s, int, float v) { sm.V[s] = v + cp.b[4][0]; });
   __syncthreads();
   if (tid < rows) V_out[row0 + tid] = sm.V[tid];
 
@@ -199,7 +247,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
     // ---- G: dV/dx through the network (tape2 of NeuralNetwork.py:162-165)
     for (int i = tid; i < S * CR_H4; i += UP_NT) {
       const int s = i / CR_H4, o = i - s * CR_H4;
-      const float w5 = __ldg(cw + L.W[4] + o);
+      const float w5 = cp.W4[o];
       sm.G[s][koff(3) + o] = w5;
       sm.DL[s][koff(3) + o] = w5 * sm.CS[s][koff(3) + o];
     }
@@ -217,7 +265,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
     __syncthreads();
     streamed<S, CR_H1>(pipe, sm, gi, &sm.DL[0][koff(1)], CW, CR_H2, g_epi(0));
     __syncthreads();
-    tile_gemm_small<S, UP_NT, 8, false>(&sm.DL[0][koff(0)], CW, CR_H1, cw + L.W[0], ns, CR_H1,
+    tile_gemm_small<S, UP_NT, 8, false>(&sm.DL[0][koff(0)], CW, CR_H1, cp.W0, ns, CR_H1,
                                         [&](int s, int j, float v) { sm.G0[s][j] = v; });
     __syncthreads();
   }
@@ -268,7 +316,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
             make_float4(-t.x * g.x * si.x, -t.y * g.y * si.y, -t.z * g.z * si.z, -t.w * g.w * si.w);
       };
     };
-    tile_gemm<S, CR_H1, UP_NT, false>(&sm.A0[0][0], NSP, ns, cw + L.W[0], CR_H1, a_epi(0));
+    tile_gemm<S, CR_H1, UP_NT, false>(&sm.A0[0][0], NSP, ns, cp.W0, CR_H1, a_epi(0));
     __syncthreads();
     streamed<S, CR_H2>(pipe, sm, gi, &sm.A[0][koff(0)], CW, CR_H1, a_epi(1));
     __syncthreads();
@@ -285,7 +333,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   // ---- B: ordinary backward through F with the injected second-order terms
   for (int i = tid; i < S * CR_H4; i += UP_NT) {
     const int s = i / CR_H4, o = i - s * CR_H4;
-    sm.G[s][koff(3) + o] += sm.VBAR[s] * __ldg(cw + L.W[4] + o) * sm.CS[s][koff(3) + o];      // e_4
+    sm.G[s][koff(3) + o] += sm.VBAR[s] * cp.W4[o] * sm.CS[s][koff(3) + o];      // e_4
   }
   for (int o = tid; o < CR_H4; o += UP_NT) {                                                   // d w5 += sum_s vbar h_4
     float acc = 0.f;
@@ -326,7 +374,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
   streamed<S, CR_H1>(pipe, sm, gi, &sm.G[0][koff(1)], CW, CR_H2, b_epi(0));
   __syncthreads();
   // layer 1
-  tile_outer2<S, CR_H1, UP_NT>(&sm.XN[0][0], NSP, &sm.G[0][koff(0)], CW, sobolev ? &sm.A0[0][0] : nullptr, NSP, &sm.DL[0][koff(0)], CW, ns,
+  tile_outer2<S, CR_H1, UP_NT>(&XN[0][0], NSP, &sm.G[0][koff(0)], CW, sobolev ? &sm.A0[0][0] : nullptr, NSP, &sm.DL[0][koff(0)], CW, ns,
                                grad + L.W[0], rows);
   tile_colsum<UP_NT>(&sm.G[0][koff(0)], CW, CR_H1, rows, grad + L.b[0]);
 }
@@ -337,6 +385,8 @@ struct ActorSmem {
   alignas(128) float WB[2 * W_CHUNK];
   uint64_t bar[2];
   WeightSeq seq;
+  ActorSmall sa;
+  CriticSmall sc;
   alignas(16) float XN[S][NSP];
   float XNP[S][NSP], G0[S][NSP];
   float H1[S][ACTOR_H], H2[S][ACTOR_H], E[S][ACTOR_H];
@@ -374,20 +424,23 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
   pipe.init(sm.WB, sm.bar);
   pipe.issue(sm.seq.ptr[0], sm.seq.first[0]);
   load_normalised<S>(P, state, row0, rows, sm.XN);
+  load_actor_small(sm.sa, aw, LA);
+  load_critic_small(sm.sc, cw, LC);
+  const CriticPtrs cp = critic_ptrs(sm.sc);
   __syncthreads();
   // ---- actor forward (NeuralNetwork.py:185)
-  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.XN[0][0], NSP, NS, aw + LA.W1, ACTOR_H, [&](int r, int c, const float4& a) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(aw + LA.b1 + c));
+  tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.XN[0][0], NSP, NS, sm.sa.W1, ACTOR_H, [&](int r, int c, const float4& a) {
+    const float4 b = *reinterpret_cast<const float4*>(sm.sa.b1 + c);
     *reinterpret_cast<float4*>(&sm.H1[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
   });
   __syncthreads();
   streamed<S, ACTOR_H>(pipe, sm, gi, &sm.H1[0][0], ACTOR_H, ACTOR_H, [&](int r, int c, const float4& a) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(aw + LA.b2 + c));
+    const float4 b = *reinterpret_cast<const float4*>(sm.sa.b2 + c);
     *reinterpret_cast<float4*>(&sm.H2[r][c]) = make_float4(leaky(a.x + b.x), leaky(a.y + b.y), leaky(a.z + b.z), leaky(a.w + b.w));
   });
   __syncthreads();
-  tile_gemm_small<S, UP_NT, 8, true>(&sm.H2[0][0], ACTOR_H, ACTOR_H, aw + LA.W3, NA, 0,
-                                     [&](int s, int j, float v) { sm.ACT[s][j] = v + __ldg(aw + LA.b3 + j); });
+  tile_gemm_small<S, UP_NT, 8, true>(&sm.H2[0][0], ACTOR_H, ACTOR_H, sm.sa.W3, NA, 0,
+                                     [&](int s, int j, float v) { sm.ACT[s][j] = v + sm.sa.b3[j]; });
   __syncthreads();
 
   // ---- per sample: s' = f(s, a), ds'/da (normalised), dr/da  (NeuralNetwork.py:188,199-204)
@@ -435,7 +488,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
   // ---- critic forward at s' keeping cos z_l, then the input-gradient sweep (NeuralNetwork.py:190-195)
   auto cf_epi = [&](int l, float* out) {
     return [&, l, out](int r, int c, const float4& a) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(cw + LC.b[l] + c));
+      const float4 b = *reinterpret_cast<const float4*>(cp.b[l] + c);
       float4 s, co;
       sincosf(a.x + b.x, &s.x, &co.x);
       sincosf(a.y + b.y, &s.y, &co.y);
@@ -447,7 +500,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
   };
   float* ch0 = &sm.CH[0][0][0];
   float* ch1 = &sm.CH[1][0][0];
-  tile_gemm<S, CR_H1, UP_NT, false>(&sm.XNP[0][0], NSP, NS, cw + LC.W[0], CR_H1, cf_epi(0, ch0));
+  tile_gemm<S, CR_H1, UP_NT, false>(&sm.XNP[0][0], NSP, NS, cp.W0, CR_H1, cf_epi(0, ch0));
   __syncthreads();
   streamed<S, CR_H2>(pipe, sm, gi, ch0, CR_H4, CR_H1, cf_epi(1, ch1));
   __syncthreads();
@@ -459,7 +512,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
   float* dl1 = &sm.DLp[1][0][0];
   for (int i = tid; i < S * CR_H4; i += UP_NT) {
     const int s = i / CR_H4, o = i - s * CR_H4;
-    dl0[s * CR_H4 + o] = __ldg(cw + LC.W[4] + o) * sm.CS[s][koff(3) + o];
+    dl0[s * CR_H4 + o] = cp.W4[o] * sm.CS[s][koff(3) + o];
   }
   __syncthreads();
   auto cg_epi = [&](int l, float* out) {
@@ -474,7 +527,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
   __syncthreads();
   streamed<S, CR_H1>(pipe, sm, gi, dl0, CR_H4, CR_H2, cg_epi(0, dl1));
   __syncthreads();
-  tile_gemm_small<S, UP_NT, 8, false>(dl1, CR_H4, CR_H1, cw + LC.W[0], NS, CR_H1, [&](int s, int j, float v) { sm.G0[s][j] = v; });
+  tile_gemm_small<S, UP_NT, 8, false>(dl1, CR_H4, CR_H1, cp.W0, NS, CR_H1, [&](int s, int j, float v) { sm.G0[s][j] = v; });
   __syncthreads();
 
   // ---- dQ/da = dV/ds' . ds'/da + dr/da ; upstream gradient on the actor output = -dQ/da / B  (:206-228)
@@ -507,7 +560,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
     const int s = i / ACTOR_H, n = i - s * ACTOR_H;
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < NA; ++j) acc = fmaf(sm.D3[s][j], __ldg(aw + LA.W3 + n * NA + j), acc);
+    for (int j = 0; j < NA; ++j) acc = fmaf(sm.D3[s][j], sm.sa.W3[n * NA + j], acc);
     sm.E[s][n] = acc * (sm.H2[s][n] > 0.f ? 1.f : LEAKY_ALPHA);
   }
   __syncthreads();
