@@ -85,7 +85,13 @@ class Network:
         np.savez(path if str(path).endswith('.npz') else str(path) + '.npz', *self.get_weights())
 
     def load_weights(self, path):
-        z = np.load(path if str(path).endswith('.npz') else str(path) + '.npz')
+        """``.npz`` written by save_weights, or a Keras ``.h5`` file written by the reference (RL.py:91-97,191-195)."""
+        path = str(path)
+        if path.endswith('.h5'):
+            from .h5weights import load_keras_weights
+            self.set_weights(load_keras_weights(path, self.ns))
+            return
+        z = np.load(path if path.endswith('.npz') else path + '.npz')
         self.set_weights([z[f'arr_{i}'] for i in range(len(self._views))])
 
     def __call__(self, x, training=True):
