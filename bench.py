@@ -32,6 +32,9 @@ ROLLOUTS_PER_GPU = 131072
 P_ACTOR_MACS = 256 * 7 + 65536 + 256 * 3          # P_a for the manipulator
 F_DYN = 250                                        # flops of the planar-3R forward dynamics step
 FLOPS_PER_ENV_STEP = 2 * P_ACTOR_MACS + F_DYN
+# dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel per launch at the default workload, from the committed
+# `ncu --set full` captures under profiles/ (None until an engine has been captured)
+TRAFFIC_BYTES = {'tf32': 8953600 + 998347520}
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
@@ -187,7 +190,7 @@ def run_b200(args):
 
     def rollout_step():      # the launches of RL_AC.rollout_batch on pre-allocated outputs (tc: W2 image refresh + rollout kernel)
         rl._launch_rollout(1, ics, hz, T, states, controls, flags, None, B)
-    launches_per_step = 2 if args.engine == 'tc' else 1
+    launches_per_step = {'tc': 3, 'tf32': 2, 'fma': 1}[args.engine]      # W2 image kernels + the rollout kernel
 
     def barrier():
         torch.cuda.synchronize()
@@ -311,11 +314,18 @@ def run_b200(args):
         peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks.get('bf16_tflops') else 'fallback 1590 TFLOP/s'
         if args.engine == 'tc':
             roof = {'bound': 'tensor', 'achieved': achieved_tflops, 'peak': bf16, 'unit': 'TFLOP/s', 'frac': achieved_tflops / bf16,
-                    'traffic': None, 'peak_source': peak_src,
+                    'traffic': TRAFFIC_BYTES.get(args.engine), 'peak_source': peak_src,
+                    'ceiling_3xfp16': bf16 / 3.0, 'frac_of_3xfp16_ceiling': achieved_tflops / (bf16 / 3.0),
+                    'note': 'k_rollout_tc16: 256x256 actor layer on tcgen05.mma kind::f16 with fp16 hi/lo operand splitting (3 UMMAs per logical '
+                            'product, fp32 accumulation in TMEM, fp32-class accuracy: parity gate 1e-5), persistent CTAs with two free-running '
+                            'tile pipelines. achieved counts ALGORITHMIC flops (2 P_a + F_dyn per env-step); the reachable ceiling is peak/3.',
+                    'flops_per_env_step': FLOPS_PER_ENV_STEP, 'kernel_ms': kernel_ms}
+        elif args.engine == 'tf32':
+            roof = {'bound': 'tensor', 'achieved': achieved_tflops, 'peak': bf16, 'unit': 'TFLOP/s', 'frac': achieved_tflops / bf16,
+                    'traffic': TRAFFIC_BYTES.get(args.engine), 'peak_source': peak_src,
                     'ceiling_3xtf32': bf16 / 6.0, 'frac_of_3xtf32_ceiling': achieved_tflops / (bf16 / 6.0),
-                    'note': 'k_rollout_tc: 256x256 actor layer on tcgen05.mma kind::tf32 with 3xTF32 operand splitting (fp32-class accuracy: parity '
-                            'gate 1e-5). achieved counts ALGORITHMIC flops (2 P_a + F_dyn per env-step); the tensor pipe executes 3 tf32 UMMAs per '
-                            'logical product and tf32 runs at half the bf16 rate, so the reachable ceiling is peak/6.',
+                    'note': 'k_rollout_tc: 256x256 actor layer on tcgen05.mma kind::tf32 with 3xTF32 operand splitting; tf32 runs at half the '
+                            'bf16 rate and 3 UMMAs are issued per logical product, so the reachable ceiling is peak/6.',
                     'flops_per_env_step': FLOPS_PER_ENV_STEP, 'kernel_ms': kernel_ms}
         else:
             roof = {'bound': 'fp32_fma', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
@@ -325,7 +335,8 @@ def run_b200(args):
         line = {
             'metric': 'manipulator rollout env-steps/s', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32 actor MLP (3xTF32 tensor cores) / f64 dynamics' if args.engine == 'tc' else 'f32 actor MLP / f64 dynamics',
+            'dtype': {'tc': 'f32 actor MLP (fp16-split x3 on tcgen05, fp32 accumulate) / f64 dynamics', 'tf32': 'f32 actor MLP (3xTF32 tensor cores) / f64 dynamics',
+                      'fma': 'f32 actor MLP / f64 dynamics'}[args.engine],
             'data': 'synthetic',
             'config': {'workload': 'BASELINE config[3]: 3-DOF planar manipulator policy rollouts (create_TO_init), '
                                    f'{B} rollouts x {T} steps per GPU (1 M over 8 GPUs), seeded-init actor {ns}->256->256->{na}',
@@ -354,7 +365,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--engine', default='tc', choices=['tc', 'fma'])
+    ap.add_argument('--engine', default='tc', choices=['tc', 'tf32', 'fma'])
     ap.add_argument('--rollouts-per-gpu', type=int, default=ROLLOUTS_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -192,14 +192,25 @@ class RL_AC:
         ICS = np.asarray(ICS, dtype=np.float64).reshape(-1, self.conf.nb_state)
         return (self.conf.NSTEPS - (ICS[:, -1] / self.conf.dt).astype(np.int64)).astype(np.int32)
 
-    # Rollout engines: 'fma' = fp32 CUDA-core kernel (cacto_rollout), 'tc' = tcgen05 3xTF32 kernel (cacto_rollout_tc).
+    # Rollout engines: 'tc' = tcgen05 fp16-split persistent kernel (cacto_rollout_tc16, default), 'tf32' = tcgen05 3xTF32
+    # kernel (cacto_rollout_tc), 'fma' = fp32 CUDA-core kernel (cacto_rollout; also runs the ep = 0 zero-control rollouts).
     rollout_engine = 'tc'
 
     def _launch_rollout(self, ep, ics, hz, T_max, states, controls, flags, rewards, B, engine=None):
         engine = engine or self.rollout_engine
+        if engine not in ('tc', 'tf32', 'fma'):
+            raise ValueError('unknown rollout engine %r' % (engine,))
         use_actor = int(ep != 0)
+        am = self.actor_model
         if use_actor and engine == 'tc':
-            am = self.actor_model
+            img = getattr(self, '_w2img16', None)
+            if img is None:
+                img = torch.empty(int(lib.cacto_actor_tc16_image_bytes()), dtype=torch.uint8, device=am.params.device)
+                self._w2img16 = img
+            check(lib.cacto_actor_tc16_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc16_prepare')
+            check(lib.cacto_rollout_tc16(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
+                                         ptr(rewards), B, stream_ptr()), 'rollout_tc16')
+        elif use_actor and engine == 'tf32':
             img = getattr(self, '_w2img', None)
             if img is None:
                 img = torch.empty(int(lib.cacto_actor_tc_image_floats()), dtype=torch.float32, device=am.params.device)
@@ -208,7 +219,7 @@ class RL_AC:
             check(lib.cacto_rollout_tc(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
                                        ptr(rewards), B, stream_ptr()), 'rollout_tc')
         else:
-            actor = self.actor_model.params if use_actor else None
+            actor = am.params if use_actor else None
             check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
                                     ptr(rewards), B, stream_ptr()), 'rollout')
 

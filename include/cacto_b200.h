@@ -126,6 +126,19 @@ int cacto_rollout_tc(const cacto_sys_params* p, const float* actor_params, const
                      const int32_t* horizon, int32_t T_max, double* states, double* controls, int32_t* flags,
                      double* rewards, int64_t B, void* stream);
 
+/* ---- K1 on tcgen05 at the fp16 rate (default rollout engine): same contract as cacto_rollout (use_actor = 1).
+ *      The 256x256 hidden layer runs as 3 x tcgen05.mma kind::f16 per K-step on fp16 hi/lo operand pairs
+ *      (a = a_hi + a_lo, w = w_hi + w_lo; a w ~= a_hi w_hi + a_hi w_lo + a_lo w_hi, fp32 accumulation in TMEM: the
+ *      accuracy class of 3xTF32 at twice the rate) by persistent CTAs that keep two 128-rollout tiles in flight.
+ *      Range limit: hidden activations beyond +-2047 overflow the fp16 high part; such a rollout is flagged failed.
+ *      w2img (cacto_actor_tc16_image_bytes() bytes, 128-byte aligned, caller-owned) is the scaled, split, UMMA-laid-out
+ *      image of the actor's W2 built by cacto_actor_tc16_prepare; rebuild it whenever the actor changes. */
+int64_t cacto_actor_tc16_image_bytes(void);
+int cacto_actor_tc16_prepare(const float* actor_params, int32_t ns, int32_t na, void* w2img, void* stream);
+int cacto_rollout_tc16(const cacto_sys_params* p, const float* actor_params, const void* w2img, const double* ics,
+                       const int32_t* horizon, int32_t T_max, double* states, double* controls, int32_t* flags,
+                       double* rewards, int64_t B, void* stream);
+
 /* ---- N4: NN.eval over a batch (NeuralNetwork.py:130-138): out[B][na] (actor) / out[B][1] (critic) */
 int cacto_actor_forward(const cacto_sys_params* p, const float* actor_params, const float* state, float* out,
                         int64_t B, void* stream);

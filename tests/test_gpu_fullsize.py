@@ -88,6 +88,10 @@ def test_config4_131072_rollouts_full_horizon():
     fma = rl.rollout_batch(X[pick], 1, horizon=hz[pick], engine='fma')
     assert float((tc['states'][:, :, pick] - fma['states']).abs().max()) < 1e-5
     assert float((tc['controls'][:, :, pick] - fma['controls']).abs().max()) < 1e-5
+    tf32 = rl.rollout_batch(X, 1, horizon=hz, engine='tf32')                                                # the two tensor-core engines, all rollouts
+    assert float((tc['states'] - tf32['states']).abs().max()) < 1e-5
+    assert float((tc['controls'] - tf32['controls']).abs().max()) < 1e-5
+    del tf32
     # two oracle rollouts (B=1 torch actor forward + NumPy RNEA per step)
     oenv = osys.make_env(conf)
     ap = onn.to_torch(rl.actor_model.get_weights())

@@ -32,9 +32,10 @@ def ics(conf, B, seed):
 
 
 @pytest.mark.parametrize('system', SYSTEM_IDS)
-@pytest.mark.parametrize('ep,engine', [(0, 'fma'), (1, 'fma'), (1, 'tc')])
+@pytest.mark.parametrize('ep,engine', [(0, 'fma'), (1, 'fma'), (1, 'tc'), (1, 'tf32')])
 def test_rollout_batch_matches_oracle(system, ep, engine):
-    """engine 'fma' = fp32 CUDA-core kernel, 'tc' = tcgen05 3xTF32 kernel (256 rollouts per CTA)."""
+    """engine 'fma' = fp32 CUDA-core kernel, 'tc' = tcgen05 fp16-split persistent kernel (default), 'tf32' = tcgen05 3xTF32
+    kernel (256 rollouts per CTA)."""
     conf, env, rl = setup(system)
     rl.rollout_engine = engine
     B = (70 if engine == 'fma' else 300) if system != 'ur5' else 5      # more than one CTA, ragged tile, mixed horizons
@@ -82,12 +83,14 @@ def test_create_TO_init_matches_reference_goldens(system):
             assert np.abs(ct - ref_c).max() <= tol * max(1.0, np.abs(ref_c).max())
 
 
-def test_tensor_core_engine_agrees_with_fma_engine():
-    """Full-size tile coverage: 1000 manipulator rollouts with mixed horizons, both engines, same actor."""
+@pytest.mark.parametrize('engine,B', [('tc', 1000), ('tf32', 1000), ('tc', 40000)])
+def test_tensor_core_engine_agrees_with_fma_engine(engine, B):
+    """Full-size tile coverage: manipulator rollouts with mixed horizons, tensor-core engine vs fp32 FMA engine, same actor.
+    B = 40000 gives the persistent 'tc' kernel 313 tiles over 148 CTAs (2-3 tiles per CTA, ragged last tile)."""
     conf, env, rl = setup('manipulator')
-    X0 = ics(conf, 1000, 7)
+    X0 = ics(conf, B, 7)
     a = rl.rollout_batch(X0, 1, engine='fma')
-    b = rl.rollout_batch(X0, 1, engine='tc')
+    b = rl.rollout_batch(X0, 1, engine=engine)
     assert bool((torch.isnan(a['states']) == torch.isnan(b['states'])).all())
     m = ~torch.isnan(a['states'])
     assert float((a['states'][m] - b['states'][m]).abs().max()) < 1e-5
@@ -96,7 +99,7 @@ def test_tensor_core_engine_agrees_with_fma_engine():
     assert bool((a['success'] == b['success']).all())
 
 
-@pytest.mark.parametrize('engine', ['fma', 'tc'])
+@pytest.mark.parametrize('engine', ['fma', 'tc', 'tf32'])
 def test_horizon_zero_and_nan_flag(engine):
     conf, env, rl = setup('manipulator')
     rl.rollout_engine = engine
