@@ -202,6 +202,8 @@ class RL_AC:
             raise ValueError('unknown rollout engine %r' % (engine,))
         use_actor = int(ep != 0)
         am = self.actor_model
+        if engine == 'tc' and am.ns > 8:
+            engine = 'tf32'        # UR5: 13 inputs exceed the fp16 kernel's shared-memory budget; its dynamics dominate anyway
         if use_actor and engine == 'tc':
             img = getattr(self, '_w2img16', None)
             if img is None:

@@ -43,10 +43,8 @@ constexpr int T16_THREADS = T16_WORKERS + 96;      // + 2 issuer warps + produce
 constexpr int T16_KC = 16;                         // hidden units per K-chunk = one kind::f16 UMMA k-step
 constexpr int T16_NCHUNK = ACTOR_H / T16_KC;       // 16
 constexpr int T16_HALF = T16_NCHUNK / 2;           // slot 1 lags by half a step
-constexpr int T16_STAGES = 3;                      // A stages per slot
-// W2 ring slots: > T16_HALF so that the slots run free; one fewer for 9..16 inputs (UR5), whose layer-1 weights and
-// exchange rows need the shared memory
-__host__ __device__ constexpr int t16_ring(int ns) { return ns > 8 ? 8 : 9; }
+constexpr int T16_STAGES = 4;                      // A stages per slot (divides T16_NCHUNK: stage and phase of a chunk are compile-time in the issuer)
+constexpr int T16_RING = 8;                        // W2 ring slots = half a step: ring slot and phase of a chunk are compile-time in the issuer
 constexpr int T16_A_IMG = T16_TILE * T16_KC * 2;   // bytes of one A image (hi or lo): 4 KB
 constexpr int T16_B_IMG = ACTOR_H * T16_KC * 2;    // bytes of one W2 image (hi or lo) of a chunk: 8 KB
 constexpr int T16_IMG_BYTES = T16_NCHUNK * 2 * T16_B_IMG;   // 256 KB
@@ -56,7 +54,7 @@ constexpr float T16_SA = 32.f;
 
 template <int NS>
 struct Tc16Smem {
-  static constexpr int RING = t16_ring(NS), XW = NS > 8 ? 16 : 8;
+  static constexpr int RING = T16_RING, XW = NS > 8 ? 16 : 8;
   alignas(1024) unsigned char B[RING][2 * T16_B_IMG];                  // W2 ring: [slot][hi | lo]           144 KB
   alignas(1024) unsigned char A[T16_SLOTS][T16_STAGES][2 * T16_A_IMG]; // A stages: [slot][stage][hi | lo]    48 KB
   alignas(16) float W1[NS][ACTOR_H];                                   // S_a * W1                           7-13 KB
@@ -77,12 +75,22 @@ __device__ __forceinline__ void t16_mbar_init(uint64_t* b, uint32_t count) {
 __device__ __forceinline__ void t16_mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-__device__ __forceinline__ void t16_mbar_wait(uint64_t* b, uint32_t parity) {
-  const uint32_t mb = smem_u32(b);
+__device__ __forceinline__ bool t16_mbar_try(uint32_t mb, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(mb), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void t16_mbar_wait_slow(uint32_t mb, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   unsigned long long t0 = 0;
   while (true) {
-    // try_wait suspends the thread in hardware for up to the hinted time (ns): waiting roles do not steal issue slots
+    // try_wait with a time hint suspends the thread in hardware (ns): waiting roles do not steal issue slots
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -98,6 +106,10 @@ __device__ __forceinline__ void t16_mbar_wait(uint64_t* b, uint32_t parity) {
       else if (now - t0 > 4000000000ull) __trap();
     }
   }
+}
+__device__ __forceinline__ void t16_mbar_wait(uint64_t* b, uint32_t parity) {
+  const uint32_t mb = smem_u32(b);
+  if (!t16_mbar_try(mb, parity)) t16_mbar_wait_slow(mb, parity);     // the common case (already complete) is one instruction
 }
 // one lane of a converged warp (the MMA / TMA roles run warp-converged on warp-uniform values so that the compiler keeps the
 // UMMA descriptors and barrier addresses in uniform registers instead of wrapping every instruction in a per-lane loop)
@@ -216,9 +228,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
   constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA, NS = NX + 1;
   constexpr int WORKERS = T16_WORKERS, THREADS = T16_THREADS;
   static_assert(NS <= 16, "the layer-1 register tile holds at most 16 inputs");
+  static_assert(T16_NCHUNK % T16_STAGES == 0 && T16_NCHUNK % T16_RING == 0 && T16_HALF % T16_RING == 0, "compile-time stage / ring indices");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   using Smem = Tc16Smem<NS>;
-  constexpr int T16_RING = Smem::RING;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const ActorLayout L(NS, NA);
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // warp: provably warp-uniform
@@ -507,36 +519,39 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
     constexpr uint32_t lboA = (T16_TILE / 8) * 128, lboB = (ACTOR_H / 8) * 128;
     const uint32_t d = tmem + (uint32_t)(m * ACTOR_H);
     const uint32_t a_base = smem_u32(&sm.A[m][0][0]), b_base = smem_u32(&sm.B[0][0]);
-    int st = 0, sphase = 0, kc = 0, rs = gb % T16_RING, rphase = (gb / T16_RING) & 1;
+    const uint32_t pb0 = (uint32_t)(gb / T16_RING) & 1u;         // ring phase of this slot's first chunk (gb is 0 or T16_HALF = T16_RING)
 #ifdef T16_TRACE
     int trace_n = 0;
 #endif
-    for (int g = gb; g < ge; ++g) {
-      T16_EV(2 + m, 1);
-      t16_mbar_wait(&sm.b_full[rs], (uint32_t)rphase);
-      T16_EV(2 + m, 2);                          // W2 chunk present
-      t16_mbar_wait(&sm.a_full[m][st], (uint32_t)sphase);
-      T16_EV(2 + m, 3);                          // A chunk present
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (t16_elect_one()) {
-        const uint64_t ah = t16_desc(a_base + (uint32_t)st * (2 * T16_A_IMG), lboA), al = t16_desc(a_base + (uint32_t)st * (2 * T16_A_IMG) + T16_A_IMG, lboA);
-        const uint64_t bh = t16_desc(b_base + (uint32_t)rs * (2 * T16_B_IMG), lboB), bl = t16_desc(b_base + (uint32_t)rs * (2 * T16_B_IMG) + T16_B_IMG, lboB);
-        t16_umma(d, ah, bh, idesc, kc == 0 ? 0u : 1u);
+    for (int g0 = gb; g0 < ge; g0 += T16_NCHUNK) {                // one step: stage = kc % 4, ring slot = kc % 8 are compile-time
+#pragma unroll
+      for (int kc = 0; kc < T16_NCHUNK; ++kc) {
+        constexpr int dummy = 0; (void)dummy;
+        const int st = kc % T16_STAGES, rs = kc % T16_RING;
+        const int g = g0 + kc;
+        T16_EV(2 + m, 1);
+        t16_mbar_wait(&sm.b_full[rs], pb0 ^ (uint32_t)((kc / T16_RING) & 1));
+        T16_EV(2 + m, 2);                        // W2 chunk present
+        t16_mbar_wait(&sm.a_full[m][st], (uint32_t)((kc / T16_STAGES) & 1));
+        T16_EV(2 + m, 3);                        // A chunk present
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (t16_elect_one()) {
+          const uint64_t ah = t16_desc(a_base + (uint32_t)st * (2 * T16_A_IMG), lboA), al = t16_desc(a_base + (uint32_t)st * (2 * T16_A_IMG) + T16_A_IMG, lboA);
+          const uint64_t bh = t16_desc(b_base + (uint32_t)rs * (2 * T16_B_IMG), lboB), bl = t16_desc(b_base + (uint32_t)rs * (2 * T16_B_IMG) + T16_B_IMG, lboB);
+          t16_umma(d, ah, bh, idesc, kc == 0 ? 0u : 1u);
 #ifndef T16_EXP_ONE_UMMA      // timing experiment only: hi x hi alone (results lose the low parts)
-        t16_umma(d, ah, bl, idesc, 1u);
-        t16_umma(d, al, bh, idesc, 1u);
+          t16_umma(d, ah, bl, idesc, 1u);
+          t16_umma(d, al, bh, idesc, 1u);
 #endif
-        t16_commit(&sm.a_empty[m][st]);                            // the A stage may be overwritten once these MMAs are done
-        if (kc == T16_NCHUNK - 1) t16_commit(&sm.d_full[m]);
-        t16_commit(&sm.b_empty[rs]);                               // my share of the ring slot
-        if (g < ob || g >= oe) t16_commit(&sm.b_empty[rs]);        // ... and the other slot's when it does not consume chunk g
-        if (m == 0 && g == T16_HALF - 1) t16_commit(&sm.start1);   // slot 1 starts half a step behind
+          t16_commit(&sm.a_empty[m][st]);                            // the A stage may be overwritten once these MMAs are done
+          if (kc == T16_NCHUNK - 1) t16_commit(&sm.d_full[m]);
+          t16_commit(&sm.b_empty[rs]);                               // my share of the ring slot
+          if (g < ob || g >= oe) t16_commit(&sm.b_empty[rs]);        // ... and the other slot's when it does not consume chunk g
+          if (kc == T16_HALF - 1 && m == 0 && g0 == 0) t16_commit(&sm.start1);   // slot 1 starts half a step behind
+        }
+        __syncwarp();
+        T16_EV(2 + m, 8);
       }
-      __syncwarp();
-      T16_EV(2 + m, 8);
-      if (++st == T16_STAGES) { st = 0; sphase ^= 1; }
-      if (++kc == T16_NCHUNK) kc = 0;
-      if (++rs == T16_RING) { rs = 0; rphase ^= 1; }
     }
   } else {
     // =================================================================== TMA producer (warp-converged, one elected lane issues)
@@ -625,7 +640,7 @@ extern "C" int cacto_rollout_tc16(const cacto_sys_params* p, const float* actor_
     case CACTO_CAR: return launch_rollout_tc16<CACTO_CAR>(*p, actor_params, img, ics, horizon, T_max, states, controls, flags, rewards, B, st);
     case CACTO_CAR_PARK: return launch_rollout_tc16<CACTO_CAR_PARK>(*p, actor_params, img, ics, horizon, T_max, states, controls, flags, rewards, B, st);
     case CACTO_MANIPULATOR: return launch_rollout_tc16<CACTO_MANIPULATOR>(*p, actor_params, img, ics, horizon, T_max, states, controls, flags, rewards, B, st);
-    case CACTO_UR5: return launch_rollout_tc16<CACTO_UR5>(*p, actor_params, img, ics, horizon, T_max, states, controls, flags, rewards, B, st);
+    case CACTO_UR5: return CACTO_E_SYSTEM;     // 13 inputs do not fit this kernel's shared-memory budget: use cacto_rollout_tc / cacto_rollout
     default: return CACTO_E_SYSTEM;
   }
 }
