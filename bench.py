@@ -34,7 +34,7 @@ F_DYN = 250                                        # flops of the planar-3R forw
 FLOPS_PER_ENV_STEP = 2 * P_ACTOR_MACS + F_DYN
 # dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel per launch at the default workload, from the committed
 # `ncu --set full` captures under profiles/ (None until an engine has been captured)
-TRAFFIC_BYTES = {'tf32': 8953600 + 998347520}
+TRAFFIC_BYTES = {'tc': 8869376 + 998446080, 'tf32': 8953600 + 998347520}
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
