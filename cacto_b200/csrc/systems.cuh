@@ -549,7 +549,7 @@ __device__ __forceinline__ void sys_ee(const cacto_sys_params& P, const T* x, T*
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
       JointRot<T> J;
-      for (int k = 0; k < 9; ++k) J.F[k] = T(P.chain.R[i][k]);
+      for (int k = 0; k < 9; ++k) J.F[k] = typename scalar_of<T>::type(P.chain.R[i][k]);
       J.axis = P.chain.axis[i];
       sincos_(x[i], J.s, J.c);
       T t[3];

@@ -139,6 +139,18 @@ int cacto_rollout_tc16(const cacto_sys_params* p, const float* actor_params, con
                        const int32_t* horizon, int32_t T_max, double* states, double* controls, int32_t* flags,
                        double* rewards, int64_t B, void* stream);
 
+/* ---- K6: TO_Casadi.backward_pass (TO.py:119-202) over a batch of ragged TO trajectories: the DDP value recursion that
+ *      produces dVdx for the Sobolev critic (TO.py:109, main.py:237-240).  Trajectory e owns knots offsets[e] .. offsets[e+1]-1
+ *      of states[n_knots][nx] (no time column, as TO.py:123-125) and controls[n_knots][na] (the row of a trajectory's last
+ *      knot is ignored).  Per knot: A, B = Env.augmented_derivative (environment.py:111-132), l_x / l_xx = gradient / Hessian
+ *      of the reward -CAMS.cost (environment_TO.py cost_fun; running weights, terminal weights at the last knot) by
+ *      hyper-dual evaluation, l_u / l_uu of the bounded control cost; then Q_*, pinv(Q_uu + mu I), V_x, V_xx
+ *      (TO.py:182-200).  V_x[n_knots][nx+1], last column 0 (TO.py:166).  workspace: caller-owned,
+ *      cacto_backward_pass_workspace_bytes(nx, na, n_knots) bytes, 8-byte aligned. */
+int64_t cacto_backward_pass_workspace_bytes(int32_t nx, int32_t na, int64_t n_knots);
+int cacto_backward_pass(const cacto_sys_params* p, const int64_t* offsets, int32_t E, const double* states,
+                        const double* controls, int64_t n_knots, double mu, void* workspace, double* V_x, void* stream);
+
 /* ---- N4: NN.eval over a batch (NeuralNetwork.py:130-138): out[B][na] (actor) / out[B][1] (critic) */
 int cacto_actor_forward(const cacto_sys_params* p, const float* actor_params, const float* state, float* out,
                         int64_t B, void* stream);
