@@ -175,10 +175,17 @@ class RL_AC:
         return _rtg_batch(self.conf, TO_states_list, TO_step_cost_list)
 
     def RL_Solve(self, TO_controls, TO_states, TO_step_cost):
-        """RL.py:145-189 for env_RL = 0 (every conf): returns the reference's 9-tuple (NumPy)."""
-        if self.conf.env_RL:
-            raise NotImplementedError('env_RL = 1 (re-simulating the TO controls) is not on the hot path; every conf sets env_RL = 0')
+        """RL.py:145-189: returns the reference's 9-tuple (NumPy).  env_RL = 0 (every conf) takes states and rewards from the
+        TO solution (:168); env_RL = 1 re-simulates the TO controls through Env.step from the stored initial state (:159-166)."""
         self.control_arr = TO_controls
+        if self.conf.env_RL:
+            T = self.NSTEPS_SH
+            rwrd_arr = np.empty(T + 1)
+            for k in range(T):
+                self.state_arr[k + 1, :], rwrd_arr[k] = self.env.step(self.conf.cost_weights_running, self.state_arr[k, :], self.control_arr[k, :])
+                self.ee_pos_arr[k + 1, :] = self.env.get_end_effector_position(self.state_arr[k + 1, :])
+            rwrd_arr[-1] = self.env.reward(self.conf.cost_weights_terminal, self.state_arr[-1, :])
+            TO_states, TO_step_cost = self.state_arr, -rwrd_arr
         out = _rtg_batch(self.conf, [TO_states], [TO_step_cost])
         self.state_arr = np.asarray(TO_states)
         rwrd_arr = -np.asarray(TO_step_cost, dtype=np.float64)

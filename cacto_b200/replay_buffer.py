@@ -167,11 +167,19 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         return s, r, s1, dv, d, term, weights, batch_idxes
 
     def update_priorities(self, idxes, reward_to_go_batch, critic_value, target_critic_value=None):
-        """replay_buffer.py:190-218 ('PER' branch)."""
+        """replay_buffer.py:190-218.  ``RB_type`` 'PER' (default: |rtg - V|) or 'ReLO' (:193-196: MSE(rtg, V) - MSE(rtg, V_target)
+        per sample, clipped to [0, max])."""
         c = self.conf
         rtg = torch.as_tensor(reward_to_go_batch).reshape(-1, 1)
         V = torch.as_tensor(critic_value).reshape(-1, 1)
-        td = torch.abs(rtg.to(torch.float32) - V.to(torch.float32))[:, 0].cpu().numpy()
+        if self.RB_type == 'ReLO':
+            Vt = torch.as_tensor(target_critic_value).reshape(-1, 1)
+            r32 = rtg.to(torch.float32)
+            td = ((r32 - V.to(torch.float32)) ** 2).mean(dim=-1) - ((r32 - Vt.to(torch.float32).to(r32.device)) ** 2).mean(dim=-1)
+            td = td.cpu().numpy()
+            td = np.clip(td, 0, np.max(td))
+        else:
+            td = torch.abs(rtg.to(torch.float32) - V.to(torch.float32))[:, 0].cpu().numpy()
         idxes = np.asarray(idxes).astype(int)
         fresh = c.fresh_factor ** self.exp_counter[idxes]
         new_p = fresh * td + c.prioritized_replay_eps

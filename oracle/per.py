@@ -178,7 +178,13 @@ class PrioritizedReplayBuffer(ReplayBuffer):
 
     def update_priorities(self, idxes, reward_to_go_batch, critic_value, target_critic_value=None):   # :190-218
         c = self.conf
-        td = np.abs(np.asarray(reward_to_go_batch, dtype=np.float32) - np.asarray(critic_value, dtype=np.float32))[:, 0]
+        if getattr(self, 'RB_type', 'PER') == 'ReLO':                # :193-196 (keras MSE, reduction NONE: mean over the last axis)
+            r = np.asarray(reward_to_go_batch, dtype=np.float32)
+            td = (((r - np.asarray(critic_value, dtype=np.float32)) ** 2).mean(axis=-1)
+                  - ((r - np.asarray(target_critic_value, dtype=np.float32)) ** 2).mean(axis=-1))
+            td = np.clip(td, 0, np.max(td))
+        else:
+            td = np.abs(np.asarray(reward_to_go_batch, dtype=np.float32) - np.asarray(critic_value, dtype=np.float32))[:, 0]
         fresh = c.fresh_factor ** self.exp_counter[idxes]
         new_p = fresh * td + c.prioritized_replay_eps
         assert len(idxes) == len(new_p)

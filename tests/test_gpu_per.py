@@ -115,3 +115,30 @@ def test_full_size_per_round_matches_oracle():
     while len(lvl) > 1:
         lvl = lvl[0::2] + lvl[1::2]
     assert lvl[0] == pb._it_sum.sum()
+
+
+def test_relo_priorities_match_oracle():
+    """RB_type = 'ReLO' (replay_buffer.py:193-196): priorities from MSE(rtg, V) - MSE(rtg, V_target), clipped at 0; trees bit-exact."""
+    from cacto_b200.replay_buffer import PrioritizedReplayBuffer
+    ns = 3
+    conf = SimpleNamespace(REPLAY_SIZE=256, BATCH_SIZE=32, nb_state=ns, prioritized_replay_alpha=0.6,
+                           prioritized_replay_beta=0.6, prioritized_replay_eps=1e-4, fresh_factor=0.95)
+    rng = np.random.default_rng(3)
+    rows = rng.normal(size=(200, 3 * ns + 3))
+    pb, ob = PrioritizedReplayBuffer(conf), oper.PrioritizedReplayBuffer(conf)
+    pb.RB_type = ob.RB_type = 'ReLO'
+    cols = (rows[:, :ns], rows[:, ns], rows[:, ns + 1:2 * ns + 1], rows[:, 2 * ns + 1:3 * ns + 1], rows[:, 3 * ns + 1], rows[:, 3 * ns + 2])
+    pb.add(*[(c,) for c in cols])
+    ob.add(*[(c,) for c in cols])
+    for r in range(3):
+        u = rng.uniform(size=32)
+        got, ref = pb.sample(u), ob.sample(u)
+        np.testing.assert_array_equal(got[7], ref[7])
+        rtg = rng.normal(size=(32, 1)).astype(np.float32)
+        V = rng.normal(size=(32, 1)).astype(np.float32)
+        Vt = rng.normal(size=(32, 1)).astype(np.float32)
+        pb.update_priorities(got[7], torch.tensor(rtg, device='cuda'), torch.tensor(V, device='cuda'), torch.tensor(Vt, device='cuda'))
+        ob.update_priorities(ref[7], rtg, V, Vt)
+        np.testing.assert_array_equal(pb._it_sum._value.cpu().numpy(), np.array(ob._it_sum.val))
+        np.testing.assert_array_equal(pb._it_min._value.cpu().numpy(), np.array(ob._it_min.val))
+        assert pb._max_priority == ob._max_priority

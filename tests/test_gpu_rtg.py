@@ -46,3 +46,36 @@ def test_ragged_batch_matches_oracle():
         np.testing.assert_array_equal(out['done'][sl].cpu().numpy(), done)
         np.testing.assert_array_equal(out['term'][sl].cpu().numpy(), term)
         assert float(out['ep_return'][e]) == ret
+
+
+def test_rl_solve_env_rl_resimulates_the_controls():
+    """env_RL = 1 (RL.py:159-166): states and rewards come from Env.step on the TO controls, then the same windows."""
+    import copy
+    from cacto_b200 import environment as genv
+    from cacto_b200.NeuralNetwork import NN
+    from cacto_b200.RL import RL_AC
+    from cacto_b200.conf import get_conf
+    from oracle import systems as osys
+    conf = copy.deepcopy(get_conf('car'))
+    conf.env_RL = 1
+    env, oenv = genv.make_env(conf), osys.make_env(conf)
+    rl = RL_AC(env, NN(env, conf, 1e-2, seed=0), conf, 0)
+    rl.setup_model()
+    rng = np.random.default_rng(4)
+    x0 = rng.uniform(conf.x_init_min, conf.x_init_max)
+    x0[-1] = (conf.NSTEPS - 12) * conf.dt
+    assert rl.create_TO_init(0, x0)[-1] == 1 and rl.NSTEPS_SH == 12
+    U = rng.uniform(conf.u_min, conf.u_max, (12, conf.nb_action))
+    got = rl.RL_Solve(U, None, None)
+    st = np.zeros((13, conf.nb_state)); st[0] = x0
+    rw = np.zeros(13)
+    for k in range(12):
+        st[k + 1], rw[k] = oenv.step(conf.cost_weights_running, st[k], U[k])
+    rw[-1] = oenv.reward(conf.cost_weights_terminal, st[-1])
+    np.testing.assert_allclose(got[0], st, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got[5], rw, rtol=1e-9, atol=1e-12)
+    _, partial, total, snext, done, rwrd, term, ret = ortg.rl_solve(conf, got[0], -got[5])
+    np.testing.assert_array_equal(got[1], partial)
+    np.testing.assert_array_equal(got[2], total)
+    np.testing.assert_array_equal(got[3], snext)
+    np.testing.assert_array_equal(got[4], done)
