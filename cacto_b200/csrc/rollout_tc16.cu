@@ -523,17 +523,24 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
 #ifdef T16_TRACE
     int trace_n = 0;
 #endif
+    // The barrier polls of chunk kc + 1 are issued before the UMMA block of chunk kc: under load an mbarrier round trip
+    // through the shared-memory pipe costs ~200 cycles, which would otherwise sit on the issuer's serial path twice per chunk.
+    bool rdy_b = t16_mbar_try(smem_u32(&sm.b_full[0]), pb0), rdy_a = t16_mbar_try(smem_u32(&sm.a_full[m][0]), 0u);
     for (int g0 = gb; g0 < ge; g0 += T16_NCHUNK) {                // one step: stage = kc % 4, ring slot = kc % 8 are compile-time
 #pragma unroll
       for (int kc = 0; kc < T16_NCHUNK; ++kc) {
-        constexpr int dummy = 0; (void)dummy;
         const int st = kc % T16_STAGES, rs = kc % T16_RING;
         const int g = g0 + kc;
         T16_EV(2 + m, 1);
-        t16_mbar_wait(&sm.b_full[rs], pb0 ^ (uint32_t)((kc / T16_RING) & 1));
+        if (!rdy_b) t16_mbar_wait_slow(smem_u32(&sm.b_full[rs]), pb0 ^ (uint32_t)((kc / T16_RING) & 1));
         T16_EV(2 + m, 2);                        // W2 chunk present
-        t16_mbar_wait(&sm.a_full[m][st], (uint32_t)((kc / T16_STAGES) & 1));
+        if (!rdy_a) t16_mbar_wait_slow(smem_u32(&sm.a_full[m][st]), (uint32_t)((kc / T16_STAGES) & 1));
         T16_EV(2 + m, 3);                        // A chunk present
+        {
+          const int kn = (kc + 1) % T16_NCHUNK;                    // next chunk (of the next step when kc = 15: same parities)
+          rdy_b = t16_mbar_try(smem_u32(&sm.b_full[kn % T16_RING]), pb0 ^ (uint32_t)((kn / T16_RING) & 1));
+          rdy_a = t16_mbar_try(smem_u32(&sm.a_full[m][kn % T16_STAGES]), (uint32_t)((kn / T16_STAGES) & 1));
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (t16_elect_one()) {
           const uint64_t ah = t16_desc(a_base + (uint32_t)st * (2 * T16_A_IMG), lboA), al = t16_desc(a_base + (uint32_t)st * (2 * T16_A_IMG) + T16_A_IMG, lboA);
