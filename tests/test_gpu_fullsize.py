@@ -106,3 +106,38 @@ def test_config4_131072_rollouts_full_horizon():
     # a second launch reproduces the first bit for bit (no atomics / races on the rollout path)
     tc2 = rl.rollout_batch(X, 1, horizon=hz, engine='tc')
     assert bool((tc2['states'] == tc['states']).all()) and bool((tc2['controls'] == tc['controls']).all())
+
+
+@pytest.mark.parametrize('system,B', [('double_integrator', 65536), ('car', 262144), ('car_park', 262144)])
+def test_config2_config3_full_size_rollouts(system, B):
+    """BASELINE configs 2 and 3: 64 k double-integrator rollouts x 200 steps, 256 k car (500 steps) / car_park rollouts in one
+    launch of the persistent tensor-core kernel; sampled rollouts agree with the fp32-FMA engine and with the oracle, every
+    knot of every rollout inside its horizon is written, nothing past it."""
+    conf, nn, rl = build(system)
+    T, ns = conf.NSTEPS, conf.nb_state
+    rng = np.random.default_rng(1)
+    X0 = rng.uniform(conf.x_init_min, conf.x_init_max, (B, ns))
+    X0[:, -1] = conf.dt * np.round(X0[:, -1] / conf.dt)
+    X0[:4, -1] = 0.0
+    tc = rl.rollout_batch(X0, 1, engine='tc')
+    hz = tc['horizon']
+    assert bool(tc['success'].all())
+    knots = torch.arange(T + 1, device='cuda')[:, None]
+    inside = knots <= hz[None, :]
+    written = ~torch.isnan(tc['states'][:, 0, :])
+    assert bool((written == inside).all())                                     # exactly the knots 0..NSTEPS_SH of every rollout
+    pick = torch.tensor([0, 1, 127, 128, 255, 256, B // 2, B - 129, B - 1], device='cuda')
+    fma = rl.rollout_batch(X0[pick.cpu().numpy()], 1, engine='fma')
+    m = ~torch.isnan(fma['states'])
+    sc = float(fma['states'][m].abs().max())
+    assert float((tc['states'][:, :, pick][m] - fma['states'][m]).abs().max()) < 1e-5 * max(1.0, sc)
+    oenv = osys.make_env(conf)
+    ap = onn.to_torch(rl.actor_model.get_weights())
+
+    def actor_eval(x):
+        with torch.no_grad():
+            return onn.actor_forward(ap, torch.tensor(x, dtype=torch.float32), conf).numpy()[0]
+    b = int(pick[6])
+    _, st, ct, Tb, ok = ortg.create_to_init(conf, oenv, actor_eval, 1, X0[b])
+    got = tc['states'][:Tb + 1, :, b].cpu().numpy()
+    assert ok and Tb == int(hz[b]) and np.abs(got - st).max() <= 1e-4 * max(1.0, np.abs(st).max())
