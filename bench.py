@@ -345,8 +345,9 @@ def run_b200(args):
                        'parallelism': f'dp{world} over independent rollouts, no collective on the rollout path'},
             'roofline': roof,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'note': 'RL_AC.rollout_to_host: kernel stores the fp64 trajectories straight into pinned host memory (zero-copy over PCIe)'},
-            'gpu_launches': K * launches_per_step,
+                    'note': 'RL_AC.rollout_to_host (pipelined): 8 sub-batches, the copy engine moves the fp64 trajectories of sub-batch k into pinned host memory '
+                            'while sub-batch k+1 is rolled out; PCIe-bound (1.06 GB per step)'},
+            'gpu_launches': K * launches_per_step,          # device-resident leg; the e2e leg launches 2 + 8 kernels per step
             'clocks': clocks,
             'extra': {'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s,
                       'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world, 'update_kernels_per_update': 6,

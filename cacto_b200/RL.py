@@ -203,7 +203,7 @@ class RL_AC:
     # kernel (cacto_rollout_tc), 'fma' = fp32 CUDA-core kernel (cacto_rollout; also runs the ep = 0 zero-control rollouts).
     rollout_engine = 'tc'
 
-    def _launch_rollout(self, ep, ics, hz, T_max, states, controls, flags, rewards, B, engine=None):
+    def _launch_rollout(self, ep, ics, hz, T_max, states, controls, flags, rewards, B, engine=None, prepare=True):
         engine = engine or self.rollout_engine
         if engine not in ('tc', 'tf32', 'fma'):
             raise ValueError('unknown rollout engine %r' % (engine,))
@@ -216,7 +216,8 @@ class RL_AC:
             if img is None:
                 img = torch.empty(int(lib.cacto_actor_tc16_image_bytes()), dtype=torch.uint8, device=am.params.device)
                 self._w2img16 = img
-            check(lib.cacto_actor_tc16_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc16_prepare')
+            if prepare:          # the W2 image follows the policy version; sub-batches of one call share it
+                check(lib.cacto_actor_tc16_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc16_prepare')
             check(lib.cacto_rollout_tc16(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
                                          ptr(rewards), B, stream_ptr()), 'rollout_tc16')
         elif use_actor and engine == 'tf32':
@@ -224,7 +225,8 @@ class RL_AC:
             if img is None:
                 img = torch.empty(int(lib.cacto_actor_tc_image_floats()), dtype=torch.float32, device=am.params.device)
                 self._w2img = img
-            check(lib.cacto_actor_tc_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc_prepare')
+            if prepare:
+                check(lib.cacto_actor_tc_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc_prepare')
             check(lib.cacto_rollout_tc(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
                                        ptr(rewards), B, stream_ptr()), 'rollout_tc')
         else:
@@ -255,19 +257,53 @@ class RL_AC:
             out['rewards'] = rewards
         return out
 
-    def rollout_to_host(self, ics_host, ep, states_host, controls_host, flags_host, mode='zero_copy', engine=None):
+    def rollout_to_host(self, ics_host, ep, states_host, controls_host, flags_host, mode='pipelined', engine=None, n_chunks=8):
         """Host-to-host rollouts for the TO feeder: ``ics_host`` [B, ns] fp64 (pinned) -> ``states_host``
         [T_max+1, ns, B], ``controls_host`` [T_max, na, B] fp64 and ``flags_host`` [B] int32 (pinned).
-        mode 'zero_copy' (default): the kernel stores the trajectories straight into the pinned host buffers over
-        PCIe (UVA), so the transfer overlaps the compute.  mode 'staged': H2D, kernel into HBM, D2H."""
+        mode 'pipelined' (default): the batch is rolled out in ``n_chunks`` sub-batches; while sub-batch k + 1 runs, the copy
+        engine moves the trajectories of sub-batch k into their columns of the host buffers (strided DMA, ~55 GB/s).
+        mode 'zero_copy': the kernel stores straight into the pinned host buffers over PCIe (UVA, ~48 GB/s).
+        mode 'staged': H2D, kernel into HBM, D2H."""
         c = self.conf
         dev = _device()
         B = ics_host.shape[0]
         T_max = int(c.NSTEPS)
+        ns, na = int(c.nb_state), int(c.nb_action)
         ics = ics_host.to(dev, non_blocking=True)
         hz_np = self.horizon(ics_host.numpy())
         hz = torch.as_tensor(hz_np).to(dev, non_blocking=True)
-        if mode == 'zero_copy':
+        if mode == 'pipelined':
+            bc = -(-B // max(1, int(n_chunks)))
+            bc = -(-bc // 128) * 128                               # whole 128-rollout tiles per sub-batch
+            st = getattr(self, '_pipe_stage', None)
+            if st is None or st['bc'] != bc:
+                st = dict(bc=bc, copy_stream=torch.cuda.Stream(device=dev),
+                          s=[torch.empty((T_max + 1) * ns * bc, dtype=torch.float64, device=dev) for _ in range(2)],
+                          u=[torch.empty(T_max * na * bc, dtype=torch.float64, device=dev) for _ in range(2)],
+                          f=[torch.empty(bc, dtype=torch.int32, device=dev) for _ in range(2)])
+                self._pipe_stage = st
+            main, side = torch.cuda.current_stream(), st['copy_stream']
+            copied = [None, None]
+            for k, b0 in enumerate(range(0, B, bc)):
+                n = min(bc, B - b0)
+                slot = k & 1
+                if copied[slot] is not None:
+                    main.wait_event(copied[slot])                  # the copy of the sub-batch that used this staging slot is done
+                sk = st['s'][slot][:(T_max + 1) * ns * n].view(T_max + 1, ns, n)
+                uk = st['u'][slot][:T_max * na * n].view(T_max, na, n)
+                fk = st['f'][slot][:n]
+                self._launch_rollout(ep, ics[b0:b0 + n], hz[b0:b0 + n], T_max, sk, uk, fk, None, n, engine, prepare=(k == 0))
+                done = torch.cuda.Event()
+                done.record(main)
+                side.wait_event(done)
+                sp = side.cuda_stream
+                check(lib.cacto_copy2d_to_host(states_host.data_ptr() + 8 * b0, 8 * B, ptr(sk), 8 * n, 8 * n, (T_max + 1) * ns, sp), 'copy2d')
+                check(lib.cacto_copy2d_to_host(controls_host.data_ptr() + 8 * b0, 8 * B, ptr(uk), 8 * n, 8 * n, T_max * na, sp), 'copy2d')
+                check(lib.cacto_copy2d_to_host(flags_host.data_ptr() + 4 * b0, 4 * n, ptr(fk), 4 * n, 4 * n, 1, sp), 'copy2d')
+                copied[slot] = torch.cuda.Event()
+                copied[slot].record(side)
+            side.synchronize()
+        elif mode == 'zero_copy':
             flags = torch.empty(B, dtype=torch.int32, device=dev)
             self._launch_rollout(ep, ics, hz, T_max, states_host, controls_host, flags, None, B, engine)
             flags_host.copy_(flags, non_blocking=True)

@@ -151,6 +151,11 @@ int64_t cacto_backward_pass_workspace_bytes(int32_t nx, int32_t na, int64_t n_kn
 int cacto_backward_pass(const cacto_sys_params* p, const int64_t* offsets, int32_t E, const double* states,
                         const double* controls, int64_t n_knots, double mu, void* workspace, double* V_x, void* stream);
 
+/* ---- plumbing for the host feeder (main.py:216-233 hands warm-starts to the TO pool): strided device-to-host copy of a
+ *      column block, rows x width_bytes, on the copy engine. */
+int cacto_copy2d_to_host(void* dst_host, int64_t dst_pitch, const void* src_dev, int64_t src_pitch, int64_t width_bytes,
+                         int64_t rows, void* stream);
+
 /* ---- N4: NN.eval over a batch (NeuralNetwork.py:130-138): out[B][na] (actor) / out[B][1] (critic) */
 int cacto_actor_forward(const cacto_sys_params* p, const float* actor_params, const float* state, float* out,
                         int64_t B, void* stream);
