@@ -63,8 +63,9 @@ struct Tc16Smem {
   alignas(16) float headx[ACTOR_H / 2][8];  // W3[.][3] | W3[.][4] | W3[.][5] | 0 (UR5)                         4 KB
   alignas(16) float4 xn[T16_SLOTS][XW / 4][T16_TILE];                  // normalised fp32 states of the step (row -> layer-1 threads) 8-16 KB
   float b3[8];
-  uint64_t b_full[RING], b_empty[RING];
-  uint64_t a_full[T16_SLOTS][T16_STAGES], a_empty[T16_SLOTS][T16_STAGES], d_full[T16_SLOTS], start1;
+  // the issuer handles K-chunks in pairs: W2 ring slots and A stages are released (and W2 is loaded) two at a time
+  uint64_t b_full[RING / 2], b_empty[RING / 2];
+  uint64_t a_full[T16_SLOTS][T16_STAGES], a_empty[T16_SLOTS][T16_STAGES / 2], d_full[T16_SLOTS], start1;
   uint32_t tmem_base;
   int tile_tmax[T16_MAXT];
 };
@@ -255,9 +256,10 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
   if (tid < 8) sm.b3[tid] = tid < NA ? actor[L.b3 + tid] : 0.f;
   for (int i = tid; i < my_tiles; i += THREADS) sm.tile_tmax[i] = 0;
   if (tid == 0) {
-    for (int s = 0; s < T16_RING; ++s) { t16_mbar_init(&sm.b_full[s], 1); t16_mbar_init(&sm.b_empty[s], 2); }
+    for (int s = 0; s < T16_RING / 2; ++s) { t16_mbar_init(&sm.b_full[s], 1); t16_mbar_init(&sm.b_empty[s], 2); }
     for (int m = 0; m < T16_SLOTS; ++m) {
-      for (int s = 0; s < T16_STAGES; ++s) { t16_mbar_init(&sm.a_full[m][s], T16_TILE / 2); t16_mbar_init(&sm.a_empty[m][s], 1); }
+      for (int s = 0; s < T16_STAGES; ++s) t16_mbar_init(&sm.a_full[m][s], T16_TILE / 2);
+      for (int s = 0; s < T16_STAGES / 2; ++s) t16_mbar_init(&sm.a_empty[m][s], 1);
       t16_mbar_init(&sm.d_full[m], 1);
     }
     t16_mbar_init(&sm.start1, 1);
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
           }
           const ulonglong2 bA = *reinterpret_cast<const ulonglong2*>(&sm.b1[c]), bB = *reinterpret_cast<const ulonglong2*>(&sm.b1[c + 4]);
           WEV(2);                                // chunk: W1 loaded, about to wait for the stage
-          if (qc >= T16_STAGES) t16_mbar_wait(&sm.a_empty[m][st], (uint32_t)((qc / T16_STAGES - 1) & 1));
+          if (qc >= T16_STAGES) t16_mbar_wait(&sm.a_empty[m][st >> 1], (uint32_t)((qc / T16_STAGES - 1) & 1));   // stage pair (st >> 1) of chunk pair qc / 2
           WEV(3);                                // stage free
           unsigned char* dst = a_dst0 + st * (2 * T16_A_IMG);
 #pragma unroll
@@ -523,38 +525,47 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
 #ifdef T16_TRACE
     int trace_n = 0;
 #endif
-    // The barrier polls of chunk kc + 1 are issued before the UMMA block of chunk kc: under load an mbarrier round trip
-    // through the shared-memory pipe costs ~200 cycles, which would otherwise sit on the issuer's serial path twice per chunk.
-    bool rdy_b = t16_mbar_try(smem_u32(&sm.b_full[0]), pb0), rdy_a = t16_mbar_try(smem_u32(&sm.a_full[m][0]), 0u);
-    for (int g0 = gb; g0 < ge; g0 += T16_NCHUNK) {                // one step: stage = kc % 4, ring slot = kc % 8 are compile-time
+    // K-chunks are issued in pairs (one fence / elect / two commits per 6 UMMAs): the issuer warp shares its scheduler with two
+    // busy worker warps and retires an instruction only every ~24 cycles, so its instruction count per chunk IS its chunk time.
+    // The barrier polls of pair kp + 1 are issued before the UMMA block of pair kp.
+    constexpr int NPAIR = T16_NCHUNK / 2, RPAIR = T16_RING / 2, SPAIR = T16_STAGES / 2;
+    bool rdy_b = t16_mbar_try(smem_u32(&sm.b_full[0]), pb0);
+    bool rdy_a0 = t16_mbar_try(smem_u32(&sm.a_full[m][0]), 0u), rdy_a1 = t16_mbar_try(smem_u32(&sm.a_full[m][1]), 0u);
+    for (int g0 = gb; g0 < ge; g0 += T16_NCHUNK) {                // one step: stages, ring slots and parities are compile-time
 #pragma unroll
-      for (int kc = 0; kc < T16_NCHUNK; ++kc) {
-        const int st = kc % T16_STAGES, rs = kc % T16_RING;
-        const int g = g0 + kc;
+      for (int kp = 0; kp < NPAIR; ++kp) {
+        const int st = (2 * kp) % T16_STAGES, rp = kp % RPAIR;
+        const int g = g0 + 2 * kp;
         T16_EV(2 + m, 1);
-        if (!rdy_b) t16_mbar_wait_slow(smem_u32(&sm.b_full[rs]), pb0 ^ (uint32_t)((kc / T16_RING) & 1));
-        T16_EV(2 + m, 2);                        // W2 chunk present
-        if (!rdy_a) t16_mbar_wait_slow(smem_u32(&sm.a_full[m][st]), (uint32_t)((kc / T16_STAGES) & 1));
-        T16_EV(2 + m, 3);                        // A chunk present
+        if (!rdy_b) t16_mbar_wait_slow(smem_u32(&sm.b_full[rp]), pb0 ^ (uint32_t)((kp / RPAIR) & 1));
+        T16_EV(2 + m, 2);                        // W2 chunk pair present
+        if (!rdy_a0) t16_mbar_wait_slow(smem_u32(&sm.a_full[m][st]), (uint32_t)((kp / SPAIR) & 1));
+        if (!rdy_a1) t16_mbar_wait_slow(smem_u32(&sm.a_full[m][st + 1]), (uint32_t)((kp / SPAIR) & 1));
+        T16_EV(2 + m, 3);                        // A chunk pair present
         {
-          const int kn = (kc + 1) % T16_NCHUNK;                    // next chunk (of the next step when kc = 15: same parities)
-          rdy_b = t16_mbar_try(smem_u32(&sm.b_full[kn % T16_RING]), pb0 ^ (uint32_t)((kn / T16_RING) & 1));
-          rdy_a = t16_mbar_try(smem_u32(&sm.a_full[m][kn % T16_STAGES]), (uint32_t)((kn / T16_STAGES) & 1));
+          const int kn = (kp + 1) % NPAIR, sn = (2 * kn) % T16_STAGES;   // next pair (of the next step when kp = 7: same parities)
+          rdy_b = t16_mbar_try(smem_u32(&sm.b_full[kn % RPAIR]), pb0 ^ (uint32_t)((kn / RPAIR) & 1));
+          rdy_a0 = t16_mbar_try(smem_u32(&sm.a_full[m][sn]), (uint32_t)((kn / SPAIR) & 1));
+          rdy_a1 = t16_mbar_try(smem_u32(&sm.a_full[m][sn + 1]), (uint32_t)((kn / SPAIR) & 1));
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (t16_elect_one()) {
-          const uint64_t ah = t16_desc(a_base + (uint32_t)st * (2 * T16_A_IMG), lboA), al = t16_desc(a_base + (uint32_t)st * (2 * T16_A_IMG) + T16_A_IMG, lboA);
-          const uint64_t bh = t16_desc(b_base + (uint32_t)rs * (2 * T16_B_IMG), lboB), bl = t16_desc(b_base + (uint32_t)rs * (2 * T16_B_IMG) + T16_B_IMG, lboB);
-          t16_umma(d, ah, bh, idesc, kc == 0 ? 0u : 1u);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t a0 = a_base + (uint32_t)(st + h) * (2 * T16_A_IMG), b0 = b_base + (uint32_t)(2 * rp + h) * (2 * T16_B_IMG);
+            const uint64_t ah = t16_desc(a0, lboA), al = t16_desc(a0 + T16_A_IMG, lboA);
+            const uint64_t bh = t16_desc(b0, lboB), bl = t16_desc(b0 + T16_B_IMG, lboB);
+            t16_umma(d, ah, bh, idesc, (kp == 0 && h == 0) ? 0u : 1u);
 #ifndef T16_EXP_ONE_UMMA      // timing experiment only: hi x hi alone (results lose the low parts)
-          t16_umma(d, ah, bl, idesc, 1u);
-          t16_umma(d, al, bh, idesc, 1u);
+            t16_umma(d, ah, bl, idesc, 1u);
+            t16_umma(d, al, bh, idesc, 1u);
 #endif
-          t16_commit(&sm.a_empty[m][st]);                            // the A stage may be overwritten once these MMAs are done
-          if (kc == T16_NCHUNK - 1) t16_commit(&sm.d_full[m]);
-          t16_commit(&sm.b_empty[rs]);                               // my share of the ring slot
-          if (g < ob || g >= oe) t16_commit(&sm.b_empty[rs]);        // ... and the other slot's when it does not consume chunk g
-          if (kc == T16_HALF - 1 && m == 0 && g0 == 0) t16_commit(&sm.start1);   // slot 1 starts half a step behind
+          }
+          t16_commit(&sm.a_empty[m][st >> 1]);                       // the A stage pair may be overwritten once these MMAs are done
+          if (kp == NPAIR - 1) t16_commit(&sm.d_full[m]);
+          t16_commit(&sm.b_empty[rp]);                               // my share of the ring slot pair
+          if (g < ob || g >= oe) t16_commit(&sm.b_empty[rp]);        // ... and the other slot's when it does not consume these chunks
+          if (kp == T16_HALF / 2 - 1 && m == 0 && g0 == 0) t16_commit(&sm.start1);   // slot 1 starts half a step behind
         }
         __syncwarp();
         T16_EV(2 + m, 8);
@@ -562,21 +573,21 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
     }
   } else {
     // =================================================================== TMA producer (warp-converged, one elected lane issues)
-    constexpr uint32_t bytes = 2 * T16_B_IMG;                      // hi + lo image of one chunk: 16 KB
-    const int gt = __shfl_sync(0xffffffffu, g_total, 0);
-    int rs = 0, rphase = 0, kc = 0;
+    constexpr uint32_t bytes = 4 * T16_B_IMG;                      // hi + lo images of two consecutive chunks: 32 KB, contiguous in the image and in the ring
+    const int gt = __shfl_sync(0xffffffffu, g_total, 0) / 2;       // chunk pairs (the ranges are multiples of T16_HALF)
+    int rp = 0, rphase = 0, kp = 0;
     for (int g = 0; g < gt; ++g) {
-      if (g >= T16_RING) t16_mbar_wait(&sm.b_empty[rs], (uint32_t)(rphase ^ 1));
+      if (g >= T16_RING / 2) t16_mbar_wait(&sm.b_empty[rp], (uint32_t)(rphase ^ 1));
       if (t16_elect_one()) {
-        const uint32_t mb = smem_u32(&sm.b_full[rs]);
+        const uint32_t mb = smem_u32(&sm.b_full[rp]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm.B[rs][0])),
-                     "l"(w2img + (size_t)kc * bytes), "r"(bytes), "r"(mb)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm.B[2 * rp][0])),
+                     "l"(w2img + (size_t)kp * bytes), "r"(bytes), "r"(mb)
                      : "memory");
       }
       __syncwarp();
-      if (++rs == T16_RING) { rs = 0; rphase ^= 1; }
-      if (++kc == T16_NCHUNK) kc = 0;
+      if (++rp == T16_RING / 2) { rp = 0; rphase ^= 1; }
+      if (++kp == T16_NCHUNK / 2) kp = 0;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
