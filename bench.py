@@ -302,6 +302,30 @@ def run_b200(args):
             graph_updates_per_s = n_gr / (a.elapsed_time(b) * 1e-3)
         except Exception as exc:           # report, do not hide
             graph_updates_per_s = f'failed: {type(exc).__name__}: {exc}'
+    # the update at the batch sizes of BASELINE configs 2 / 3 (PER batch 4096, critic batch 16384), single GPU, eager launches
+    large_batch = {}
+    if world == 1:
+        for Bl in (4096, 16384):
+            gl = torch.Generator(device='cpu').manual_seed(Bl)
+            sl = (lo + (hi - lo) * torch.rand((Bl, ns), generator=gl, dtype=torch.float64)).float().to(dev)
+            snl = (lo + (hi - lo) * torch.rand((Bl, ns), generator=gl, dtype=torch.float64)).float().to(dev)
+            prl = (-5 * torch.rand((Bl, 1), generator=gl)).to(dev)
+            dvl = torch.randn((Bl, ns), generator=gl).to(dev); dvl[:, -1] = 0
+            dl = (torch.rand((Bl, 1), generator=gl) < 0.5).float().to(dev)
+            tl = (torch.rand((Bl, 1), generator=gl) < 0.01).double().to(dev)
+            wl = torch.ones((Bl, 1), device=dev)
+            for _ in range(5):
+                rl.update(sl, snl, prl, dvl, dl, tl, wl, fuse_target=True)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(30):
+                rl.update(sl, snl, prl, dvl, dl, tl, wl, fuse_target=True)
+            b.record(stream)
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) * 1e3 / 30
+            large_batch[str(Bl)] = {'us_per_update': us, 'samples_per_s': Bl / (us * 1e-6),
+                                    'algorithmic_tflops': Bl * 0.994e6 / (us * 1e-6) / 1e12}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -351,7 +375,7 @@ def run_b200(args):
             'clocks': clocks,
             'extra': {'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s,
                       'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world, 'update_kernels_per_update': 6,
-                      'fp32_fma_peak_tflops_measured': fma_peak_tflops},
+                      'fp32_fma_peak_tflops_measured': fma_peak_tflops, 'sobolev_update_large_batch': large_batch},
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu
