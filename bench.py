@@ -92,14 +92,14 @@ def run_reference(args):
     rate = total_steps / total_dt
     sample = (f'{cores * per_core} rollouts x 100 steps per bench step ({total_steps} env-steps in {total_dt:.1f} s), t0 = 0; oracle port '
               f'(B=1 torch-CPU actor forward + NumPy fp64 RNEA dynamics per step) over multiprocessing.Pool({cores})')
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': 'manipulator rollout env-steps/s', 'value': rate, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_dt / max(1, args.steps), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 actor / f64 dynamics', 'data': 'synthetic',
         'config': {'workload': 'BASELINE config[3]: manipulator policy rollouts (RL.py:221-231 structure), CPU', 'sample': sample},
         'cpu_baseline': {'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': rate, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
+        'gpu_launches': 0})
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -379,12 +379,29 @@ def run_b200(args):
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints to fd 1 during the run
+    (NCCL writes its version banner there) has been redirected to stderr."""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the duration of the run
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)

@@ -135,6 +135,43 @@ def env_goldens():
         np.savez_compressed(os.path.join(HERE, f'env_{s}.npz'), **out)
 
 
+# ------------------------------------------------------------------------------------ TO backward pass
+def backward_pass_goldens():
+    """TO_Casadi.backward_pass (TO.py:119-202) executed UNMODIFIED, together with the reference's *_CAMS cost models
+    (environment_TO.py) and Env.augmented_derivative (environment.py), on top of the symbolic stub of _casadi_stub.py.
+    Only the systems whose models need no Pinocchio: single integrator and car."""
+    import importlib
+    import _casadi_stub
+    _casadi_stub.install()
+    import environment as ref_env
+    import environment_TO as ref_env_TO
+    importlib.reload(ref_env_TO)
+    import TO as ref_TO
+    importlib.reload(ref_TO)
+    rng = np.random.default_rng(77)
+    out = {}
+    for s, cams in (('single_integrator', 'SingleIntegrator_CAMS'), ('car', 'Car_CAMS')):
+        conf = _ref_stubs.import_conf(s)
+        env = getattr(ref_env, ENV_CLASS[s])(conf)
+        to = ref_TO.TO_Casadi(env, conf, getattr(ref_env_TO, cams), w_S=1e-2)
+        to.runningSingleModel = to.CAMS('running_model', conf)          # TO.py:43,45 (set inside TO_System_Solve)
+        to.terminalModel = to.CAMS('terminal_model', conf)
+        n, m = conf.nb_state - 1, conf.nb_action
+        for k, T in enumerate((2, 9, 17)):
+            x = rng.uniform(np.asarray(conf.x_init_min[:-1], float), np.asarray(conf.x_init_max[:-1], float))
+            X, U = [x], []
+            for _ in range(T - 1):
+                u = rng.uniform(np.asarray(conf.u_min, float), np.asarray(conf.u_max, float)) * 0.3
+                U.append(u)
+                X.append(np.asarray(env.simulate(np.append(X[-1], 0.0), u), dtype=float)[:-1])
+            X, U = np.array(X), np.array(U).reshape(-1, m)
+            Vx = to.backward_pass(T, X, U)
+            out[f'{s}_{k}_X'], out[f'{s}_{k}_U'], out[f'{s}_{k}_Vx'] = X, U, np.asarray(Vx, dtype=float)
+            # the cost model itself, on the same knots: -cost must be the reward (environment_TO.py vs environment.py)
+            out[f'{s}_{k}_cost'] = np.array([float(to.runningSingleModel.cost(X[t], U[min(t, T - 2)])) for t in range(T)])
+    np.savez_compressed(os.path.join(HERE, 'bp_cases.npz'), **out)
+
+
 # ------------------------------------------------------------------------------------ PER
 def _buffer_conf(R, B, ns, alpha=0.6, beta=0.6, eps=1e-2, fresh=0.95):
     return types.SimpleNamespace(REPLAY_SIZE=R, BATCH_SIZE=B, nb_state=ns, prioritized_replay_alpha=alpha,
@@ -353,6 +390,7 @@ if __name__ == '__main__':
     urdf_tables()
     env_goldens()
     per_goldens()
+    backward_pass_goldens()
     rtg_goldens()
     toinit_goldens()
     h5_goldens()

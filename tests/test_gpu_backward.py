@@ -59,3 +59,22 @@ def test_backward_pass_pinv_handles_zero_control_weight():
     ref = obw.backward_pass(oenv, len(X), X, U)
     sc = np.abs(ref).max(axis=0) + 1e-9
     assert (np.abs(got - ref) / sc).max() < 1e-6
+
+
+@pytest.mark.parametrize('system', ['single_integrator', 'car'])
+def test_backward_pass_matches_reference_goldens(system):
+    """The reference's own backward_pass (tests/golden/bp_cases.npz, see make_golden.backward_pass_goldens)."""
+    from conftest import golden
+    from cacto_b200 import environment as genv
+    from cacto_b200.TO import TO_Casadi
+    g = golden('bp_cases.npz')
+    conf = get_conf(system)
+    to = TO_Casadi(genv.make_env(conf), conf, None, w_S=1e-2)
+    Xs = [g[f'{system}_{k}_X'] for k in range(3)]
+    Us = [g[f'{system}_{k}_U'] for k in range(3)]
+    Vx, off = to.backward_pass_batch(Xs, Us)
+    Vx = Vx.cpu().numpy()
+    for k in range(3):
+        ref = g[f'{system}_{k}_Vx']
+        sc = np.abs(ref).max(axis=0) + 1e-9
+        assert (np.abs(Vx[off[k]:off[k + 1]] - ref) / sc).max() < 1e-6

@@ -81,3 +81,21 @@ def test_backward_pass_equals_gradient_of_the_lq_value_for_the_double_integrator
     Quu = l_uu + B.T @ V_xx @ B + 1e-9 * np.eye(2)
     ref = (l_x + A.T @ g_T) - (A.T @ V_xx @ B) @ np.linalg.solve(Quu, l_u + B.T @ g_T)
     np.testing.assert_allclose(Vx[-2, :-1], ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('system', ['single_integrator', 'car'])
+def test_backward_pass_matches_the_reference_run_on_the_casadi_stub(system):
+    """tests/golden/bp_cases.npz: the reference's own TO_Casadi.backward_pass + *_CAMS cost models + Env.augmented_derivative,
+    executed unmodified on tests/golden/_casadi_stub.py (exact hyper-dual derivatives instead of CasADi's symbolic ones)."""
+    from conftest import golden
+    g = golden('bp_cases.npz')
+    conf = get_conf(system)
+    env = osys.make_env(conf)
+    for k in range(3):
+        X, U, ref = g[f'{system}_{k}_X'], g[f'{system}_{k}_U'], g[f'{system}_{k}_Vx']
+        got = obw.backward_pass(env, len(X), X, U)
+        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-11)
+        # the reference's cost model is the negative reward (running weights, bounded control cost)
+        for t in range(len(X)):
+            u = U[min(t, len(X) - 2)] if len(U) else np.zeros(conf.nb_action)
+            assert -g[f'{system}_{k}_cost'][t] == pytest.approx(obw.reward_generic(env, conf.cost_weights_running, list(X[t]), list(u)), rel=1e-12, abs=1e-12)
