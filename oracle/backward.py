@@ -1,12 +1,12 @@
 """CPU restatement of ``TO_Casadi.backward_pass`` (TO.py:119-202) -- ORACLE, test infrastructure only.
 
 The reference differentiates ``running_cost = -runningSingleModel.cost(x, u)`` (TO.py:147-164) with CasADi
-(``casadi==3.6.3``, absent here).  Pinning: for the single integrator and the car (the systems whose models need no
+(``casadi==3.6.3``, absent here).  Pinning: for the single integrator, the car and car_park (the systems whose models need no
 Pinocchio) the reference's OWN ``TO_Casadi.backward_pass`` + ``*_CAMS`` cost models + ``Env.augmented_derivative`` were
 executed unmodified in the build container on a small symbolic stand-in for CasADi (tests/golden/_casadi_stub.py: expression
 graph, exact hyper-dual derivatives) -> tests/golden/bp_cases.npz; this module reproduces those V_x to 1e-9 and the cost
-values to 1e-12 (tests/test_oracle_backward.py).  Double integrator, car_park, manipulator, UR5: PARITY UNPINNED (their CAMS
-models need pinocchio.casadi / casadi matrix algebra); covered by the checks listed below.  ``-cost`` is the reward of environment.py with the
+values to 1e-12 (tests/test_oracle_backward.py).  Double integrator, manipulator, UR5: PARITY UNPINNED (their CAMS
+models need pinocchio.casadi); covered by the checks listed below.  ``-cost`` is the reward of environment.py with the
 running / terminal weights (environment_TO.py:90-111 SI, :208-234 DI, :339-360 car, :479-503 car_park, :605-631
 manipulator, :735-765 UR5 -- each the negative of the matching ``Env.reward``, with the bounded control cost
 ``a^2 + w_b (a/u_max)^10`` for every system including UR5, quirk Q8).  Here the same expression is evaluated on

@@ -63,9 +63,20 @@ def _num(op, *v):
     raise NotImplementedError(op)
 
 
+_UFUNC = {'add': 'add', 'subtract': 'sub', 'multiply': 'mul', 'true_divide': 'div', 'divide': 'div', 'power': 'pow', 'negative': 'neg',
+          'log': 'log', 'exp': 'exp', 'sqrt': 'sqrt', 'cos': 'cos', 'sin': 'sin', 'tan': 'tan'}
+
+
+def _apply(op, *a):
+    a = [float(x) if isinstance(x, (np.floating, np.integer)) or (isinstance(x, np.ndarray) and x.ndim == 0 and x.dtype != object) else
+         (x.item() if isinstance(x, np.ndarray) and x.ndim == 0 else x) for x in a]
+    if not any(isinstance(x, E) for x in a):
+        return _num(op, *a)
+    return E(op, *[E.wrap(x) for x in a])
+
+
 class E:
-    """Scalar expression node."""
-    __array_priority__ = 1000
+    """Scalar expression node.  Containers (casadi.SX n x 1, matrices) are plain NumPy object arrays of E / floats."""
 
     def __init__(self, op, *args):
         self.op, self.args = op, args
@@ -73,6 +84,14 @@ class E:
     @staticmethod
     def wrap(x):
         return x if isinstance(x, E) else E('const', float(x))
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != '__call__' or ufunc.__name__ not in _UFUNC:
+            return NotImplemented
+        op = _UFUNC[ufunc.__name__]
+        if any(isinstance(i, np.ndarray) and i.ndim > 0 for i in inputs):
+            return np.frompyfunc(lambda *a: _apply(op, *a), len(inputs), 1)(*inputs)
+        return _apply(op, *inputs)
 
     def ev(self, env):
         if self.op == 'const':
@@ -83,20 +102,25 @@ class E:
             fn, k, argv = self.args
             inner = {}
             for sym_vec, arg in zip(fn.inputs, argv):
-                for s, a in zip(sym_vec.items, arg.items):
-                    inner[s.args[0]] = a.ev(env)
-            return fn.outputs[0].items[k].ev(inner)
+                for s_, a in zip(sym_vec, arg):
+                    inner[s_.args[0]] = _ev(a, env)
+            return _ev(fn.outputs[0][k], inner)
         return _num(self.op, *[a.ev(env) for a in self.args])
 
-    def __add__(self, o): return E('add', self, E.wrap(o))
-    def __radd__(self, o): return E('add', E.wrap(o), self)
-    def __sub__(self, o): return E('sub', self, E.wrap(o))
-    def __rsub__(self, o): return E('sub', E.wrap(o), self)
-    def __mul__(self, o): return E('mul', self, E.wrap(o))
-    def __rmul__(self, o): return E('mul', E.wrap(o), self)
-    def __truediv__(self, o): return E('div', self, E.wrap(o))
-    def __rtruediv__(self, o): return E('div', E.wrap(o), self)
-    def __pow__(self, n): return E('pow', self, E.wrap(n))
+    def _b(self, op, o, swap=False):
+        if isinstance(o, np.ndarray) and o.ndim > 0:
+            return np.frompyfunc((lambda x: _apply(op, x, self)) if swap else (lambda x: _apply(op, self, x)), 1, 1)(o)
+        return _apply(op, o, self) if swap else _apply(op, self, o)
+
+    def __add__(self, o): return self._b('add', o)
+    def __radd__(self, o): return self._b('add', o, True)
+    def __sub__(self, o): return self._b('sub', o)
+    def __rsub__(self, o): return self._b('sub', o, True)
+    def __mul__(self, o): return self._b('mul', o)
+    def __rmul__(self, o): return self._b('mul', o, True)
+    def __truediv__(self, o): return self._b('div', o)
+    def __rtruediv__(self, o): return self._b('div', o, True)
+    def __pow__(self, n): return self._b('pow', n)
     def __neg__(self): return E('neg', self)
     def log(self): return E('log', self)
     def exp(self): return E('exp', self)
@@ -106,25 +130,17 @@ class E:
     def tan(self): return E('tan', self)
 
 
-class Vec:
-    """Column vector of scalar expressions (casadi.SX n x 1)."""
+def _ev(x, env):
+    return x.ev(env) if isinstance(x, E) else float(x)
 
-    def __init__(self, items):
-        self.items = list(items)
 
-    def __len__(self): return len(self.items)
-
-    def __getitem__(self, k):
-        if isinstance(k, slice):
-            return Vec(self.items[k])
-        return self.items[k]
-
-    def __setitem__(self, k, v):
-        if isinstance(k, slice):
-            vals = v.items if isinstance(v, Vec) else list(v)
-            self.items[k] = [E.wrap(x) for x in vals]
-        else:
-            self.items[k] = E.wrap(v)
+def _vec(x):
+    """1-D object array view of a symbolic vector / scalar / list."""
+    if isinstance(x, E):
+        a = np.empty(1, dtype=object)
+        a[0] = x
+        return a
+    return np.asarray(x, dtype=object).reshape(-1)
 
 
 class Deriv:
@@ -137,67 +153,81 @@ class Deriv:
 class _SX:
     def __call__(self, n, m=1):
         assert m == 1
-        return Vec([E('const', 0.0) for _ in range(n)])
+        a = np.empty(n, dtype=object)
+        a[:] = 0.0
+        return a
 
     @staticmethod
     def sym(name, n, m=1):
         assert m == 1
-        return Vec([E('sym', (name, i, id(object()))) for i in range(n)])
+        a = np.empty(n, dtype=object)
+        for i in range(n):
+            a[i] = E('sym', (name, i, id(a)))
+        return a
 
 
 class Function:
     def __init__(self, name, inputs, outputs, *names):
-        self.name, self.inputs = name, inputs
-        self.outputs = [o if isinstance(o, (Vec, Deriv)) else Vec([o]) for o in outputs]
+        self.name, self.inputs = name, [_vec(i) for i in inputs]
+        self.outputs = [o if isinstance(o, Deriv) else _vec(o) for o in outputs]
 
     def __call__(self, *args):
-        symbolic = any(isinstance(a, Vec) or isinstance(a, E) for a in args)
+        symbolic = any(isinstance(a, E) or (isinstance(a, np.ndarray) and a.dtype == object) for a in args)
         out = self.outputs[0]
         if symbolic:
-            argv = [a if isinstance(a, Vec) else Vec([a]) for a in args]
-            assert isinstance(out, Vec)
-            res = Vec([E('call', self, k, argv) for k in range(len(out))])
-            return res if len(res) > 1 else res.items[0]
+            argv = [_vec(a) for a in args]
+            assert not isinstance(out, Deriv)
+            res = np.empty(len(out), dtype=object)
+            for k in range(len(out)):
+                res[k] = E('call', self, k, argv)
+            return res if len(res) > 1 else res[0]
         vals = [np.asarray(a, dtype=float).reshape(-1) for a in args]
         env = {}
         for sv, v in zip(self.inputs, vals):
-            for s, x in zip(sv.items, v):
-                env[s.args[0]] = float(x)
-        if isinstance(out, Vec):
-            return np.array([[o.ev(env)] for o in out.items], dtype=float)
-        xs = out.x.items
+            for s_, x in zip(sv, v):
+                env[s_.args[0]] = float(x)
+        if not isinstance(out, Deriv):
+            return np.array([[_ev(o, env)] for o in out], dtype=float)
+        xs = _vec(out.x)
         n = len(xs)
         if out.kind in ('grad', 'hess'):
             g, H = np.zeros(n), np.zeros((n, n))
             for i in range(n):
                 for j in range(i, n):
                     e2 = dict(env)
-                    for k, s in enumerate(xs):
-                        e2[s.args[0]] = HD(env.get(s.args[0], 0.0), 1.0 if k == i else 0.0, 1.0 if k == j else 0.0)
-                    r = _lift(out.expr.ev(e2))
+                    for k, s_ in enumerate(xs):
+                        e2[s_.args[0]] = HD(env.get(s_.args[0], 0.0), 1.0 if k == i else 0.0, 1.0 if k == j else 0.0)
+                    r = _lift(_ev(out.expr, e2))
                     H[i, j] = H[j, i] = r.ab
                     if i == j:
                         g[i] = r.a
             return g.reshape(n, 1) if out.kind == 'grad' else H
-        us = out.u.items
+        us = _vec(out.u)
         M = np.zeros((n, len(us)))
         for i in range(n):
             for j in range(len(us)):
                 e2 = dict(env)
                 e2[xs[i].args[0]] = HD(env.get(xs[i].args[0], 0.0), 1.0, 0.0)
                 e2[us[j].args[0]] = HD(env.get(us[j].args[0], 0.0), 0.0, 1.0)
-                M[i, j] = _lift(out.expr.ev(e2)).ab
+                M[i, j] = _lift(_ev(out.expr, e2)).ab
         return M
 
 
+def _scalar(expr):
+    if isinstance(expr, np.ndarray):
+        assert expr.size == 1
+        return expr.reshape(-1)[0]
+    return expr
+
+
 def hessian(expr, x):
-    return Deriv('hess', expr, x), Deriv('grad', expr, x)
+    return Deriv('hess', _scalar(expr), x), Deriv('grad', _scalar(expr), x)
 
 
 def jacobian(expr, x):
     if isinstance(expr, Deriv) and expr.kind == 'grad':
         return Deriv('mixed', expr.expr, expr.x, x)
-    return Deriv('grad', expr, x)
+    return Deriv('grad', _scalar(expr), x)
 
 
 def install():
@@ -210,5 +240,10 @@ def install():
     m.cos = lambda e: E.wrap(e).cos()
     m.sin = lambda e: E.wrap(e).sin()
     m.tan = lambda e: E.wrap(e).tan()
+    m.horzcat = lambda *a: np.array(list(a), dtype=object).reshape(1, -1)
+    m.vertcat = lambda *a: np.vstack([np.atleast_2d(np.asarray(x, dtype=object)) for x in a])
+    m.mtimes = lambda a, b: np.dot(np.asarray(a, dtype=object), np.asarray(b, dtype=object))
+    m.repmat = lambda a, r, c: np.tile(np.atleast_2d(np.asarray(a, dtype=object)), (r, c))
+    m.sum1 = lambda a: np.sum(np.asarray(a, dtype=object), axis=0)
     sys.modules['casadi'] = m
     return m

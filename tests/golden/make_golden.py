@@ -139,7 +139,7 @@ def env_goldens():
 def backward_pass_goldens():
     """TO_Casadi.backward_pass (TO.py:119-202) executed UNMODIFIED, together with the reference's *_CAMS cost models
     (environment_TO.py) and Env.augmented_derivative (environment.py), on top of the symbolic stub of _casadi_stub.py.
-    Only the systems whose models need no Pinocchio: single integrator and car."""
+    Only the systems whose models need no Pinocchio: single integrator, car and car_park."""
     import importlib
     import _casadi_stub
     _casadi_stub.install()
@@ -150,7 +150,7 @@ def backward_pass_goldens():
     importlib.reload(ref_TO)
     rng = np.random.default_rng(77)
     out = {}
-    for s, cams in (('single_integrator', 'SingleIntegrator_CAMS'), ('car', 'Car_CAMS')):
+    for s, cams in (('single_integrator', 'SingleIntegrator_CAMS'), ('car', 'Car_CAMS'), ('car_park', 'CarPark_CAMS')):
         conf = _ref_stubs.import_conf(s)
         env = getattr(ref_env, ENV_CLASS[s])(conf)
         to = ref_TO.TO_Casadi(env, conf, getattr(ref_env_TO, cams), w_S=1e-2)
@@ -159,6 +159,8 @@ def backward_pass_goldens():
         n, m = conf.nb_state - 1, conf.nb_action
         for k, T in enumerate((2, 9, 17)):
             x = rng.uniform(np.asarray(conf.x_init_min[:-1], float), np.asarray(conf.x_init_max[:-1], float))
+            if s == 'car_park':                  # v and delta are 0 in the init box; spread them
+                x[3], x[4] = rng.uniform(-2, 2), rng.uniform(-0.4, 0.4)
             X, U = [x], []
             for _ in range(T - 1):
                 u = rng.uniform(np.asarray(conf.u_min, float), np.asarray(conf.u_max, float)) * 0.3

@@ -61,7 +61,7 @@ def test_backward_pass_pinv_handles_zero_control_weight():
     assert (np.abs(got - ref) / sc).max() < 1e-6
 
 
-@pytest.mark.parametrize('system', ['single_integrator', 'car'])
+@pytest.mark.parametrize('system', ['single_integrator', 'car', 'car_park'])
 def test_backward_pass_matches_reference_goldens(system):
     """The reference's own backward_pass (tests/golden/bp_cases.npz, see make_golden.backward_pass_goldens)."""
     from conftest import golden

@@ -83,7 +83,7 @@ def test_backward_pass_equals_gradient_of_the_lq_value_for_the_double_integrator
     np.testing.assert_allclose(Vx[-2, :-1], ref, rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize('system', ['single_integrator', 'car'])
+@pytest.mark.parametrize('system', ['single_integrator', 'car', 'car_park'])
 def test_backward_pass_matches_the_reference_run_on_the_casadi_stub(system):
     """tests/golden/bp_cases.npz: the reference's own TO_Casadi.backward_pass + *_CAMS cost models + Env.augmented_derivative,
     executed unmodified on tests/golden/_casadi_stub.py (exact hyper-dual derivatives instead of CasADi's symbolic ones)."""
