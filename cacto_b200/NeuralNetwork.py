@@ -11,8 +11,9 @@ reference uses: ``trainable_variables`` / ``variables``, ``get_weights`` / ``set
 
 The regularisers the reference attaches to its layers are inert there (gradients are taken of the loss
 only, ``model.losses`` is never added: SURVEY.md quirk Q6) and are therefore not represented.
-Only the default critic ('sine', every conf) is on the hot path; the elu / relu / sine-elu variants are
-listed as next work in DESIGN.md and raise here.
+The default critic ('sine', every conf) runs on the fused tiled kernels of csrc/update.cu; the elu / relu / sine-elu
+variants (NeuralNetwork.py:65-93,110-128) run on the generic one-CTA-per-sample kernels of csrc/mlp_generic.cu
+(``Network.kind == 'critic_generic'``), with the same methods and return values.
 """
 import math
 
@@ -28,18 +29,26 @@ CRITIC_HIDDEN = (64, 64, 128, 128)
 
 class Network:
     """A dense network stored as one flat float32 block (+ its per-layer transposed copy and a gradient
-    accumulator).  kind: 'actor' (LeakyReLU 0.3) or 'critic_sine'."""
+    accumulator).  kind: 'actor' (LeakyReLU 0.3), 'critic_sine', or 'critic_generic' (any layer table, ``acts`` per layer:
+    'sin' | 'elu' | 'leaky' | 'linear'; no transposed copy)."""
 
     _registry = {}
 
-    def __init__(self, kind, ns, na, dims):
+    def __init__(self, kind, ns, na, dims, acts=None):
         self.kind, self.ns, self.na, self.dims = kind, int(ns), int(na), list(dims)
         self.n = sum(i * o + o for i, o in zip(dims[:-1], dims[1:]))
-        expect = lib.cacto_critic_param_count(self.ns) if kind == 'critic_sine' else lib.cacto_actor_param_count(self.ns, self.na)
-        assert self.n == expect, (self.n, expect)
+        if acts is None:
+            acts = (['leaky'] * (len(dims) - 2) if kind == 'actor' else ['sin'] * (len(dims) - 2)) + ['linear']
+        self.acts = list(acts)
+        self.desc = _lib.make_mlp_desc(self.dims, self.acts)
         dev = _device()
         self.params = torch.zeros(self.n, dtype=torch.float32, device=dev)
-        self.params_T = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        if kind == 'critic_generic':
+            self.params_T = None
+        else:
+            expect = lib.cacto_critic_param_count(self.ns) if kind == 'critic_sine' else lib.cacto_actor_param_count(self.ns, self.na)
+            assert self.n == expect, (self.n, expect)
+            self.params_T = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self._views = self._make_views(self.params)
         self._grad_views = self._make_views(self.grad)
@@ -77,6 +86,8 @@ class Network:
         self.refresh_transposed()
 
     def refresh_transposed(self):
+        if self.params_T is None:
+            return
         check(lib.cacto_transpose_params(ptr(self.params), ptr(self.params_T), self.is_critic, self.ns, self.na, stream_ptr()),
               'transpose_params')
 
@@ -140,10 +151,34 @@ class NN:
         net.set_weights(w)
         return net
 
-    def create_critic_elu(self):
-        raise NotImplementedError("critic_type 'elu' is not on the GPU hot path yet (every reference conf uses 'sine')")
+    def _generic_critic(self, hidden, acts, siren):
+        """Dense stack ns -> hidden... -> 1 on the generic kernels.  Keras default initialisers (glorot-uniform kernel, zero
+        bias) except for the tf_siren layers (kernel U(+-sqrt(6/fan_in)), bias he_uniform), as in create_critic_sine."""
+        c = self.conf
+        net = Network('critic_generic', c.nb_state, c.nb_action, [c.nb_state] + list(hidden) + [1], list(acts) + ['linear'])
+        w = []
+        for l, (i, o) in enumerate(zip(net.dims[:-1], net.dims[1:])):
+            if l < len(hidden) and siren[l]:
+                lk, lb = math.sqrt(6.0 / i), math.sqrt(6.0 / o)
+                w += [self._rng.uniform(-lk, lk, (i, o)).astype(np.float32), self._rng.uniform(-lb, lb, o).astype(np.float32)]
+            else:
+                w += [_glorot(self._rng, i, o), np.zeros(o, np.float32)]
+        net.set_weights(w)
+        return net
 
-    create_critic_sine_elu = create_critic_relu = create_critic_elu
+    def create_critic_elu(self):
+        """NeuralNetwork.py:65-78: Dense 16, 32, 256, 256 with elu, Dense(1)."""
+        return self._generic_critic((16, 32, 256, 256), ['elu'] * 4, [False] * 4)
+
+    def create_critic_sine_elu(self):
+        """NeuralNetwork.py:80-93: SIREN(64), Dense(64, elu), SIREN(128), Dense(128, elu), Dense(1)."""
+        return self._generic_critic((64, 64, 128, 128), ['sin', 'elu', 'sin', 'elu'], [True, False, True, False])
+
+    def create_critic_relu(self):
+        """NeuralNetwork.py:110-128: Dense 16, 32, NH1, NH2 each followed by LeakyReLU() (alpha 0.3), Dense(1); the
+        regularisers are inert (quirks Q6, Q14)."""
+        c = self.conf
+        return self._generic_critic((16, 32, c.NH1, c.NH2), ['leaky'] * 4, [False] * 4)
 
     # -- forward ------------------------------------------------------------------------------
     def eval(self, NN, input):
@@ -155,6 +190,10 @@ class NN:
         if NN.kind == 'actor':
             out = torch.empty((B, NN.na), dtype=torch.float32, device=x.device)
             check(lib.cacto_actor_forward(self._p, ptr(NN.params), ptr(x), ptr(out), B, stream_ptr()), 'actor_forward')
+        elif NN.kind == 'critic_generic':
+            out = torch.empty((B, 1), dtype=torch.float32, device=x.device)
+            check(lib.cacto_mlp_forward_generic(self._p, _lib.C.byref(NN.desc), ptr(NN.params), ptr(x), ptr(out), ptr(None), B, stream_ptr()),
+                  'mlp_forward_generic')
         else:
             out = torch.empty((B, 1), dtype=torch.float32, device=x.device)
             check(lib.cacto_critic_forward(self._p, ptr(NN.params), ptr(x), ptr(out), ptr(None), B, stream_ptr()), 'critic_forward')
@@ -166,8 +205,47 @@ class NN:
         B = x.shape[0]
         V = torch.empty((B, 1), dtype=torch.float32, device=x.device)
         dV = torch.empty((B, critic.ns), dtype=torch.float32, device=x.device)
-        check(lib.cacto_critic_forward(self._p, ptr(critic.params), ptr(x), ptr(V), ptr(dV), B, stream_ptr()), 'critic_forward')
+        if critic.kind == 'critic_generic':
+            check(lib.cacto_mlp_forward_generic(self._p, _lib.C.byref(critic.desc), ptr(critic.params), ptr(x), ptr(V), ptr(dV), B, stream_ptr()),
+                  'mlp_forward_generic')
+        else:
+            check(lib.cacto_critic_forward(self._p, ptr(critic.params), ptr(x), ptr(V), ptr(dV), B, stream_ptr()), 'critic_forward')
         return V, dV
+
+    # -- gradient launches (shared by the eager methods below and by RL_AC's CUDA-graph update) -----------
+    def launch_critic_grad(self, cm, tc, s, sn, pr, dv, d, w, inv_B, rtg, V, Vt, B):
+        if cm.kind == 'critic_generic':
+            check(lib.cacto_critic_grad_generic(self._p, _lib.C.byref(cm.desc), ptr(cm.params), ptr(tc.params), float(self.w_S),
+                                                int(bool(self.conf.MC)), ptr(s), ptr(sn), ptr(pr), ptr(dv), ptr(d), ptr(w), inv_B, ptr(cm.grad),
+                                                ptr(rtg), ptr(V), ptr(Vt), ptr(self.last_critic_loss), B, stream_ptr()), 'critic_grad_generic')
+        else:
+            check(lib.cacto_critic_grad(self._p, ptr(cm.params), ptr(cm.params_T), ptr(tc.params), float(self.w_S), int(bool(self.conf.MC)),
+                                        ptr(s), ptr(sn), ptr(pr), ptr(dv), ptr(d), ptr(w), inv_B, ptr(cm.grad), ptr(rtg), ptr(V), ptr(Vt),
+                                        ptr(self.last_critic_loss), B, stream_ptr()), 'critic_grad')
+
+    def launch_actor_grad(self, am, cm, s, term, inv_B, actions, B):
+        if cm.kind == 'critic_generic':
+            # environment terms from the batched kernels of the reference-facing API (NeuralNetwork.py:185-204), network part generic
+            act = self.eval(am, s)
+            s_next = self.env.simulate_batch(s, act)
+            Fu = self.env.derivative_batch(s, act)
+            if getattr(self, '_w_rt', None) is None:
+                c = self.conf
+                self._w_rt = (torch.zeros(8, dtype=torch.float64, device=s.device), torch.zeros(8, dtype=torch.float64, device=s.device))
+                wr, wt = np.zeros(8), np.zeros(8)
+                wr[:len(c.cost_weights_running)] = c.cost_weights_running
+                wt[:len(c.cost_weights_terminal)] = c.cost_weights_terminal
+                self._w_rt[0].copy_(torch.as_tensor(wr)); self._w_rt[1].copy_(torch.as_tensor(wt))
+            tm = term.reshape(-1, 1)
+            w8 = tm * self._w_rt[1][None, :] + (1.0 - tm) * self._w_rt[0][None, :]                 # NeuralNetwork.py:201
+            dr_da = self.env.reward_batch_da(w8, s, act)
+            if actions is not None:
+                actions.copy_(act)
+            check(lib.cacto_actor_grad_generic(self._p, _lib.C.byref(am.desc), ptr(am.params), _lib.C.byref(cm.desc), ptr(cm.params), ptr(s),
+                                               ptr(s_next), ptr(Fu), ptr(dr_da), inv_B, ptr(am.grad), B, stream_ptr()), 'actor_grad_generic')
+        else:
+            check(lib.cacto_actor_grad(self._p, ptr(am.params), ptr(am.params_T), ptr(cm.params), ptr(cm.params_T), ptr(s), ptr(term), inv_B,
+                                       ptr(am.grad), ptr(actions), B, stream_ptr()), 'actor_grad')
 
     def custom_logarithm(self, input):
         """NeuralNetwork.py:140-148."""
@@ -196,10 +274,7 @@ class NN:
         critic_model.grad.zero_()
         self.last_critic_loss.zero_()
         inv_B = 1.0 / float(global_batch if global_batch is not None else B)
-        check(lib.cacto_critic_grad(self._p, ptr(critic_model.params), ptr(critic_model.params_T), ptr(target_critic.params),
-                                    float(self.w_S), int(bool(self.conf.MC)), ptr(s), ptr(sn), ptr(pr), ptr(dv), ptr(d), ptr(w), inv_B,
-                                    ptr(critic_model.grad), ptr(rtg), ptr(V), ptr(Vt), ptr(self.last_critic_loss), B, stream_ptr()),
-              'critic_grad')
+        self.launch_critic_grad(critic_model, target_critic, s, sn, pr, dv, d, w, inv_B, rtg, V, Vt, B)
         return critic_model._grad_views, rtg, V, Vt
 
     def compute_actor_grad(self, actor_model, critic_model, state_batch, term_batch, batch_size, global_batch=None, return_actions=False):
@@ -213,9 +288,7 @@ class NN:
         actions = torch.empty((B, actor_model.na), dtype=torch.float32, device=s.device) if return_actions else None
         actor_model.grad.zero_()
         inv_B = 1.0 / float(global_batch if global_batch is not None else B)
-        check(lib.cacto_actor_grad(self._p, ptr(actor_model.params), ptr(actor_model.params_T), ptr(critic_model.params),
-                                   ptr(critic_model.params_T), ptr(s), ptr(term), inv_B, ptr(actor_model.grad), ptr(actions), B,
-                                   stream_ptr()), 'actor_grad')
+        self.launch_actor_grad(actor_model, critic_model, s, term, inv_B, actions, B)
         if return_actions:
             return actor_model._grad_views, actions
         return actor_model._grad_views

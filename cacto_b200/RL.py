@@ -115,18 +115,15 @@ class RL_AC:
         inv_B = 1.0 / float(B * world)
         cm, tc, am = self.critic_model, self.target_critic, self.actor_model
         self.critic_optimizer.prepare(cm.params.device, zero=nn.last_critic_loss)
-        check(lib.cacto_critic_grad(self.env._p, ptr(cm.params), ptr(cm.params_T), ptr(tc.params), float(nn.w_S), int(bool(c.MC)),
-                                    ptr(io['state']), ptr(io['state_next']), ptr(io['partial_rtg']), ptr(io['dVdx']), ptr(io['done']),
-                                    ptr(io['weights']), inv_B, ptr(cm.grad), ptr(io['rtg']), ptr(io['V']), ptr(io['V_target']),
-                                    ptr(nn.last_critic_loss), B, stream_ptr()), 'critic_grad')
+        nn.launch_critic_grad(cm, tc, io['state'], io['state_next'], io['partial_rtg'], io['dVdx'], io['done'], io['weights'], inv_B,
+                              io['rtg'], io['V'], io['V_target'], B)
         self._allreduce(cm)
         if c.MC:
             self.critic_optimizer.step(cm, prepared=True)
         else:
             self.critic_optimizer.step(cm, target=tc, tau=c.UPDATE_RATE, prepared=True)
         self.actor_optimizer.prepare(am.params.device)
-        check(lib.cacto_actor_grad(self.env._p, ptr(am.params), ptr(am.params_T), ptr(cm.params), ptr(cm.params_T), ptr(io['state']),
-                                   ptr(io['term']), inv_B, ptr(am.grad), ptr(None), B, stream_ptr()), 'actor_grad')
+        nn.launch_actor_grad(am, cm, io['state'], io['term'], inv_B, None, B)
         self._allreduce(am)
         self.actor_optimizer.step(am, prepared=True)
 
@@ -365,7 +362,7 @@ class UpdateGraph:
         for n in nets:
             n.grad.zero_()
         # snapshot the training state, warm up on a side stream (lazy initialisation), capture, restore
-        snap = [(t, t.clone()) for n in nets for t in (n.params, n.params_T)]
+        snap = [(t, t.clone()) for n in nets for t in (n.params, n.params_T) if t is not None]
         snap += [(t, t.clone()) for o in opts for st in o._state.values() for t in st]
         snap += [(o._dev['step'], o._dev['step'].clone()) for o in opts]
         its = [o.iterations for o in opts]

@@ -106,6 +106,10 @@ _SIGNATURES = {
     'cacto_backward_pass': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
     'cacto_copy2d_to_host': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    'cacto_mlp_forward_generic': (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]),
+    'cacto_critic_grad_generic': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_int] + [C.c_void_p] * 6 + [C.c_float] + [C.c_void_p] * 5 +
+                                  [C.c_int64, C.c_void_p]),
+    'cacto_actor_grad_generic': (C.c_int, [C.c_void_p] * 9 + [C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_actor_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_critic_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_critic_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 6 +
@@ -127,6 +131,25 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+MLP_MAX_LAYERS = 8
+ACT_CODES = {'linear': 0, 'sin': 1, 'elu': 2, 'leaky': 3}
+
+
+class MlpDesc(C.Structure):
+    """cacto_mlp_desc of include/cacto_b200.h."""
+    _fields_ = [('n_layers', C.c_int32), ('dims', C.c_int32 * (MLP_MAX_LAYERS + 1)), ('act', C.c_int32 * MLP_MAX_LAYERS)]
+
+
+def make_mlp_desc(dims, acts):
+    assert len(acts) == len(dims) - 1 <= MLP_MAX_LAYERS
+    d = MlpDesc()
+    d.n_layers = len(acts)
+    for i, v in enumerate(dims):
+        d.dims[i] = int(v)
+    for i, a in enumerate(acts):
+        d.act[i] = ACT_CODES[a]
+    return d
 
 
 def load_library(path=LIB_PATH):

@@ -906,7 +906,13 @@ extern "C" int cacto_adam_step(float* params, float* grad, float* m, float* v, f
   if (!params || !grad || !m || !v) return CACTO_E_ARG;
   int64_t total = 0;
   LayerTable T = make_table(is_critic, ns, na, &total);
-  if (n != total) return CACTO_E_SIZE;
+  if (params_T_or_null == nullptr) {          // no transposed copy to refresh (generic networks): any flat block of n parameters
+    if (n < 0) return CACTO_E_SIZE;
+    if (n == 0) return 0;
+    T.n = 0;
+  } else if (n != total) {
+    return CACTO_E_SIZE;
+  }
   k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, m, v, alpha_t, alpha_dev_or_null, 1.f - beta1, 1.f - beta2, eps,
                                                                        target_or_null, tau, params_T_or_null, T, n);
   CACTO_LAUNCH_CHECK();

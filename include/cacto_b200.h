@@ -156,6 +156,31 @@ int cacto_backward_pass(const cacto_sys_params* p, const int64_t* offsets, int32
 int cacto_copy2d_to_host(void* dst_host, int64_t dst_pitch, const void* src_dev, int64_t src_pitch, int64_t width_bytes,
                          int64_t rows, void* stream);
 
+/* ---- Generic dense networks: the critic variants of NeuralNetwork.py besides 'sine' (create_critic_elu :65-78,
+ *      create_critic_sine_elu :80-93, create_critic_relu :110-128), or any stack of <= CACTO_MLP_MAX_LAYERS dense layers of
+ *      <= 256 units.  Parameter block in Keras order [W1 (in x out), b1, ...]; act[l] is the activation after layer l (the last
+ *      one CACTO_ACT_LINEAR).  One CTA per sample (latency-oriented); same semantics, arguments and outputs as
+ *      cacto_critic_forward / cacto_critic_grad / cacto_actor_grad, without the transposed parameter copies. */
+#define CACTO_MLP_MAX_LAYERS 8
+enum { CACTO_ACT_LINEAR = 0, CACTO_ACT_SIN = 1, CACTO_ACT_ELU = 2, CACTO_ACT_LEAKY = 3 };
+typedef struct cacto_mlp_desc {
+  int32_t n_layers;                          /* dense layers L */
+  int32_t dims[CACTO_MLP_MAX_LAYERS + 1];    /* dims[0] = nb_state, dims[L] = outputs */
+  int32_t act[CACTO_MLP_MAX_LAYERS];
+} cacto_mlp_desc;
+int cacto_mlp_forward_generic(const cacto_sys_params* p, const cacto_mlp_desc* d, const float* params, const float* state,
+                              float* out, float* dout_ds, int64_t B, void* stream);
+int cacto_critic_grad_generic(const cacto_sys_params* p, const cacto_mlp_desc* d, const float* critic_params,
+                              const float* target_params, float w_S, int mc, const float* state, const float* state_next,
+                              const float* partial_rtg, const float* dVdx, const float* done, const float* weights, float inv_B,
+                              float* grad, float* rtg, float* V, float* V_target_s, float* loss, int64_t B, void* stream);
+/* state_next = Env.simulate_batch(state, actor(state)), Fu = Env.derivative_batch (normalised, [B][ns][na]) and
+ * dr_da = d reward_batch / d action come from cacto_dyn_step / cacto_dyn_derivative / cacto_reward (NeuralNetwork.py:185-204). */
+int cacto_actor_grad_generic(const cacto_sys_params* p, const cacto_mlp_desc* d_actor, const float* actor_params,
+                             const cacto_mlp_desc* d_critic, const float* critic_params, const float* state,
+                             const float* state_next, const float* Fu, const float* dr_da, float inv_B, float* grad, int64_t B,
+                             void* stream);
+
 /* ---- N4: NN.eval over a batch (NeuralNetwork.py:130-138): out[B][na] (actor) / out[B][1] (critic) */
 int cacto_actor_forward(const cacto_sys_params* p, const float* actor_params, const float* state, float* out,
                         int64_t B, void* stream);
@@ -182,7 +207,8 @@ int cacto_actor_grad(const cacto_sys_params* p, const float* actor_params, const
  *      p -= alpha_t m / (sqrt(v) + eps)) fused with the optional Polyak target update (RL.py:113-118:
  *      target = tau p + (1-tau) target), the refresh of the transposed copy and the zeroing of `grad`.
  *      alpha_t = lr(t-1) sqrt(1-b2^t)/(1-b1^t) is computed by the caller. n must equal the network's
- *      parameter count. */
+ *      parameter count; with params_T_or_null == NULL (generic networks, no transposed copy) any flat block of n
+ *      parameters is accepted and is_critic / ns / na are ignored. */
 int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_t, const float* alpha_dev_or_null,
                     float beta1, float beta2, float eps, float* target_or_null, float tau, float* params_T_or_null,
                     int32_t is_critic, int32_t ns, int32_t na, int64_t n, void* stream);

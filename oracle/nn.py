@@ -66,11 +66,28 @@ def actor_forward(p, s, conf):
     return h @ p[4] + p[5]
 
 
+def critic_spec(conf):
+    """(hidden widths, activation per hidden layer, is-SIREN per hidden layer) of conf.critic_type:
+    NeuralNetwork.py:95-108 'sine', :65-78 'elu', :80-93 'sine-elu', :110-128 'relu' (LeakyReLU() = alpha 0.3)."""
+    t = getattr(conf, 'critic_type', 'sine')
+    if t == 'sine':
+        return CRITIC_HIDDEN, ('sin',) * 4, (True,) * 4
+    if t == 'elu':
+        return (16, 32, 256, 256), ('elu',) * 4, (False,) * 4
+    if t == 'sine-elu':
+        return (64, 64, 128, 128), ('sin', 'elu', 'sin', 'elu'), (True, False, True, False)
+    return (16, 32, conf.NH1, conf.NH2), ('leaky',) * 4, (False,) * 4
+
+
+_ACT = {'sin': torch.sin, 'elu': torch.nn.functional.elu, 'leaky': lambda z: torch.nn.functional.leaky_relu(z, 0.3)}
+
+
 def critic_forward(p, s, conf):
     x = normalize(s, conf.state_norm_arr) if conf.NORMALIZE_INPUTS else s
+    acts = critic_spec(conf)[1]
     h = x
     for l in range(4):
-        h = torch.sin(h @ p[2 * l] + p[2 * l + 1])
+        h = _ACT[acts[l]](h @ p[2 * l] + p[2 * l + 1])
     return h @ p[8] + p[9]
 
 
