@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) k_tc16_prepare(const float* __restrict__ 
   }
 }
 
-#ifdef T16_TRACE   // debug builds only (scratch/): per-role event timeline of CTA 0 (code in the low byte, clock64 above)
+#ifdef T16_TRACE   // debug builds only (profiles/scripts/): per-role event timeline of CTA 0 (code in the low byte, clock64 above)
 __device__ long long* g_t16_trace = nullptr;
 constexpr int T16_TRACE_N = 8192;
 #define T16_EV(role, code)                                                                                       \
@@ -214,7 +214,7 @@ constexpr int T16_TRACE_N = 8192;
 
 // ---------------------------------------------------------------------------------------------------------------
 // tcgen05.ld.16x256b.x2: 16 TMEM lanes x 16 columns.  Register 4k + 2rh + e of thread t holds lane (t / 4 + 8 rh),
-// column 8k + 2 (t % 4) + e  (k = 0..1; layout verified on B200 with scratch/ldtm_test.cu).
+// column 8k + 2 (t % 4) + e  (k = 0..1; layout verified on B200 with profiles/scripts/ldtm_test.cu).
 #define T16_LDTM_16x256_X2(v, taddr)                                                                     \
   asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                 \
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
