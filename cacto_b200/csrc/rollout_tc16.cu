@@ -87,6 +87,9 @@ __device__ __forceinline__ bool t16_mbar_try(uint32_t mb, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+#ifndef T16_WAIT_HINT_NS
+#define T16_WAIT_HINT_NS 20000
+#endif
 __device__ __noinline__ void t16_mbar_wait_slow(uint32_t mb, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   unsigned long long t0 = 0;
@@ -97,7 +100,7 @@ __device__ __noinline__ void t16_mbar_wait_slow(uint32_t mb, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(mb), "r"(parity), "r"(20000u)
+        : "r"(mb), "r"(parity), "r"((uint32_t)T16_WAIT_HINT_NS)
         : "memory");
     if (done) break;
     if ((++spins & 1023u) == 0) {              // fail loudly instead of hanging the GPU: trap after 4 s
