@@ -19,17 +19,26 @@ import torch
 from ._lib import check, lib, ptr, stream_ptr
 from .environment import _as_cuda, _device
 from .optim import Adam, PiecewiseConstantDecay
-from .parallel import allreduce_sum
+from .parallel import PeerReduce, PeerRegion, allreduce_sum
 from .rtg import rtg_batch as _rtg_batch
 
 
 class RL_AC:
-    def __init__(self, env, NN, conf, N_try, dist=None):
+    def __init__(self, env, NN, conf, N_try, dist=None, reduce='peer', peer_region=None, peer_max_ctas=0):
+        """``dist``: the initialised ``torch.distributed`` module (or an object with its get_rank / get_world_size / broadcast
+        surface) for the data-parallel update over the GPUs of one box; ``reduce``: 'peer' sums the gradient blocks over NVLink
+        peer memory inside the Adam kernel (parallel.PeerReduce), 'nccl' launches one all-reduce per network before it;
+        ``peer_region``: a ready ``PeerRegion`` (tests simulate several ranks on one GPU with ``PeerRegion.local_group``)."""
         self.env = env
         self.NN = NN
         self.conf = conf
         self.N_try = N_try
         self.dist = dist
+        if reduce not in ('peer', 'nccl'):
+            raise ValueError('unknown gradient reduction %r' % (reduce,))
+        self.reduce = reduce
+        self._peer_region, self._peer_max_ctas = peer_region, peer_max_ctas
+        self._peer = None
 
         self.actor_model = None
         self.critic_model = None
@@ -79,10 +88,21 @@ class RL_AC:
             for net in (self.actor_model, self.critic_model, self.target_critic):
                 self.dist.broadcast(net.params, src=0)
                 net.refresh_transposed()
+            if self.reduce == 'peer' and self.dist.get_world_size() > 1 and self.actor_model.params.is_cuda:
+                region = self._peer_region
+                if region is None:
+                    region = PeerRegion.exchange(PeerReduce.region_bytes(self.critic_model.n, self.actor_model.n), self.dist)
+                self._peer = PeerReduce(region, self.critic_model, self.actor_model, max_ctas=self._peer_max_ctas)
 
     # ------------------------------------------------------------------------------ update
-    def _allreduce(self, net):
-        allreduce_sum(net.grad, self.dist)             # NCCL sum over NVLink; each rank used 1/global_batch
+    def _reduce_and_step(self, opt, net, other, target=None, tau=0.0, prepared=False):
+        """Sum the per-rank gradient blocks (each rank used 1/global_batch) and apply the Adam step: one kernel over NVLink
+        peer memory, or an NCCL all-reduce followed by the single-GPU kernel."""
+        if self._peer is not None:
+            opt.step(net, target=target, tau=tau, prepared=prepared, peer=self._peer.table(net), zero_other=other.grad)
+        else:
+            allreduce_sum(net.grad, self.dist)
+            opt.step(net, target=target, tau=tau, prepared=prepared)
 
     def update(self, state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
                batch_size=None, fuse_target=False):
@@ -94,15 +114,20 @@ class RL_AC:
         critic_grad, reward_to_go_batch, critic_value, target_critic_value = self.NN.compute_critic_grad(
             self.critic_model, self.target_critic, state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch,
             weights_batch, global_batch=gb)
-        self._allreduce(self.critic_model)
-        if fuse_target and not self.conf.MC:
+        if world > 1:
+            fused = fuse_target and not self.conf.MC
+            self._reduce_and_step(self.critic_optimizer, self.critic_model, self.actor_model, self.target_critic if fused else None,
+                                  self.conf.UPDATE_RATE if fused else 0.0)
+        elif fuse_target and not self.conf.MC:
             self.critic_optimizer.step(self.critic_model, target=self.target_critic, tau=self.conf.UPDATE_RATE)
         else:
             self.critic_optimizer.apply_gradients(zip(critic_grad, self.critic_model.trainable_variables))
 
         actor_grad = self.NN.compute_actor_grad(self.actor_model, self.critic_model, state_batch, term_batch, batch_size, global_batch=gb)
-        self._allreduce(self.actor_model)
-        self.actor_optimizer.apply_gradients(zip(actor_grad, self.actor_model.trainable_variables))
+        if world > 1:
+            self._reduce_and_step(self.actor_optimizer, self.actor_model, self.critic_model)
+        else:
+            self.actor_optimizer.apply_gradients(zip(actor_grad, self.actor_model.trainable_variables))
         return reward_to_go_batch, critic_value, target_critic_value
 
     # ------------------------------------------------------------------------------ CUDA-graph update
@@ -117,15 +142,13 @@ class RL_AC:
         self.critic_optimizer.prepare(cm.params.device, zero=nn.last_critic_loss)
         nn.launch_critic_grad(cm, tc, io['state'], io['state_next'], io['partial_rtg'], io['dVdx'], io['done'], io['weights'], inv_B,
                               io['rtg'], io['V'], io['V_target'], B)
-        self._allreduce(cm)
         if c.MC:
-            self.critic_optimizer.step(cm, prepared=True)
+            self._reduce_and_step(self.critic_optimizer, cm, am, prepared=True)
         else:
-            self.critic_optimizer.step(cm, target=tc, tau=c.UPDATE_RATE, prepared=True)
+            self._reduce_and_step(self.critic_optimizer, cm, am, target=tc, tau=c.UPDATE_RATE, prepared=True)
         self.actor_optimizer.prepare(am.params.device)
         nn.launch_actor_grad(am, cm, io['state'], io['term'], inv_B, None, B)
-        self._allreduce(am)
-        self.actor_optimizer.step(am, prepared=True)
+        self._reduce_and_step(self.actor_optimizer, am, cm, prepared=True)
 
     def make_update_graph(self, batch_size=None):
         """Capture update + update_target for a fixed batch size into a CUDA graph.  Returns an ``UpdateGraph`` whose
@@ -202,11 +225,11 @@ class RL_AC:
 
     def _launch_rollout(self, ep, ics, hz, T_max, states, controls, flags, rewards, B, engine=None, prepare=True):
         engine = engine or self.rollout_engine
-        if engine not in ('tc', 'tf32', 'fma'):
+        if engine not in ('tc', 'tc2', 'tf32', 'fma'):
             raise ValueError('unknown rollout engine %r' % (engine,))
         use_actor = int(ep != 0)
         am = self.actor_model
-        if engine == 'tc' and am.ns > 8:
+        if engine in ('tc', 'tc2') and am.ns > 8:
             engine = 'tf32'        # UR5: 13 inputs exceed the fp16 kernel's shared-memory budget; its dynamics dominate anyway
         if use_actor and engine == 'tc':
             img = getattr(self, '_w2img16', None)
@@ -217,6 +240,15 @@ class RL_AC:
                 check(lib.cacto_actor_tc16_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc16_prepare')
             check(lib.cacto_rollout_tc16(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
                                          ptr(rewards), B, stream_ptr()), 'rollout_tc16')
+        elif use_actor and engine == 'tc2':
+            img = getattr(self, '_w2img16p', None)
+            if img is None:
+                img = torch.empty(int(lib.cacto_actor_tc16p_image_bytes()), dtype=torch.uint8, device=am.params.device)
+                self._w2img16p = img
+            if prepare:
+                check(lib.cacto_actor_tc16p_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc16p_prepare')
+            check(lib.cacto_rollout_tc16p(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
+                                          ptr(rewards), B, stream_ptr()), 'rollout_tc16p')
         elif use_actor and engine == 'tf32':
             img = getattr(self, '_w2img', None)
             if img is None:

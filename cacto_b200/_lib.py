@@ -110,6 +110,18 @@ _SIGNATURES = {
     'cacto_critic_grad_generic': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_int] + [C.c_void_p] * 6 + [C.c_float] + [C.c_void_p] * 5 +
                                   [C.c_int64, C.c_void_p]),
     'cacto_actor_grad_generic': (C.c_int, [C.c_void_p] * 9 + [C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_actor_tc16p_image_bytes': (C.c_int64, []),
+    'cacto_actor_tc16p_prepare': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    'cacto_rollout_tc16p': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_adam_step_peer': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    'cacto_peer_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    'cacto_peer_free': (C.c_int, [C.c_void_p]),
+    'cacto_peer_export': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'cacto_peer_open': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'cacto_peer_close': (C.c_int, [C.c_void_p]),
     'cacto_actor_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_critic_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_critic_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 6 +

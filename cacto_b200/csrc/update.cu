@@ -699,7 +699,35 @@ struct LayerTable {
   int in[5], out[5];
 };
 
-// p -= alpha * m / (sqrt(v) + eps) with m += (g - m)(1 - b1), v += (g^2 - v)(1 - b2)   
+// index of parameter i inside the per-layer transposed copy (weights [in][out] -> [out][in], biases unchanged)
+__device__ __forceinline__ int64_t transposed_index(const LayerTable& T, int64_t i) {
+  for (int l = 0; l < T.n; ++l) {
+    const int64_t sz = (int64_t)T.in[l] * T.out[l];
+    if (i >= T.W[l] && i < T.W[l] + sz) {
+      const int64_t e = i - T.W[l];
+      const int r = (int)(e / T.out[l]), c = (int)(e - (int64_t)r * T.out[l]);
+      return T.W[l] + (int64_t)c * T.in[l] + r;
+    }
+  }
+  return i;
+}
+
+// p -= alpha * m / (sqrt(v) + eps) with m += (g - m)(1 - b1), v += (g^2 - v)(1 - b2)   (SURVEY.md A.5), the Polyak target
+// update (RL.py:116-118) and the refresh of the transposed copy, for parameter i with gradient gi
+__device__ __forceinline__ void adam_element(int64_t i, float gi, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float alpha,
+                                             float omb1, float omb2, float eps, float* __restrict__ target, float tau, float* __restrict__ pT,
+                                             const LayerTable& T) {
+  float mi = m[i], vi = v[i];
+  mi += (gi - mi) * omb1;
+  vi += (gi * gi - vi) * omb2;
+  m[i] = mi;
+  v[i] = vi;
+  const float pi = p[i] - (mi * alpha) / (sqrtf(vi) + eps);
+  p[i] = pi;
+  if (target != nullptr) target[i] = pi * tau + target[i] * (1.f - tau);
+  if (pT != nullptr) pT[transposed_index(T, i)] = pi;
+}
+
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                               float alpha, const float* __restrict__ alpha_dev, float omb1, float omb2, float eps,
                                               float* __restrict__ target, float tau,
@@ -708,44 +736,84 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __re
   if (i >= n) return;
   const float gi = g[i];
   g[i] = 0.f;
-  float mi = m[i], vi = v[i];
-  mi += (gi - mi) * omb1;
-  vi += (gi * gi - vi) * omb2;
-  m[i] = mi;
-  v[i] = vi;
   if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);     // device-side schedule (CUDA-graph replays)
-  const float pi = p[i] - (mi * alpha) / (sqrtf(vi) + eps);
-  p[i] = pi;
-  if (target != nullptr) target[i] = pi * tau + target[i] * (1.f - tau);      // RL.py:116-118
-  if (pT != nullptr) {
-    int64_t j = i;
-    for (int l = 0; l < T.n; ++l) {
-      const int64_t sz = (int64_t)T.in[l] * T.out[l];
-      if (i >= T.W[l] && i < T.W[l] + sz) {
-        const int64_t e = i - T.W[l];
-        const int r = (int)(e / T.out[l]), c = (int)(e - (int64_t)r * T.out[l]);
-        j = T.W[l] + (int64_t)c * T.in[l] + r;
-        break;
+  adam_element(i, gi, p, m, v, alpha, omb1, omb2, eps, target, tau, pT, T);
+}
+
+// ---- data-parallel update: the gradient all-reduce fused into the Adam step over NVLink peer memory.
+// Every rank keeps its gradient sums in a CUDA-IPC region mapped by all ranks of the box.  The kernel (i) announces "my
+// gradients of launch number `epoch` are complete" with one system-scope release store into the flag word [rank] of every peer,
+// (ii) waits until the flag words of all peers in its own region have reached `epoch`, (iii) sums the W gradient blocks in
+// rank order 0..W-1 with peer loads through NVSwitch -- the same order on every rank, so the replicas stay bit-identical --
+// and applies Adam / Polyak / the transposed refresh.  The rank's own gradient block cannot be cleared here (peers may
+// still be reading it); instead the kernel clears `zero_other`, the gradient block of the OTHER network: every peer has
+// finished reading that block before it announced the step this kernel has just waited for (critic and actor steps
+// alternate, RL.py:104-109).  Replaces two NCCL all-reduce launches per update by two flag round trips.
+struct PeerTable {
+  const float* grad[CACTO_MAX_PEERS];   // gradient block of every rank (own block included), peer-mapped
+  unsigned* flags[CACTO_MAX_PEERS];     // flag words [CACTO_MAX_PEERS] of every rank
+  int world, rank;
+};
+
+__global__ void __launch_bounds__(256) k_adam_peer(float* __restrict__ p, PeerTable R, float* __restrict__ zero_other, int64_t n_other,
+                                                   float* __restrict__ m, float* __restrict__ v, const float* __restrict__ alpha_dev, float omb1,
+                                                   float omb2, float eps, float* __restrict__ target, float tau, float* __restrict__ pT,
+                                                   LayerTable T, int64_t n) {
+  // words [0, CACTO_MAX_PEERS) of a rank's flag row: arrival epochs written by the peers; [CACTO_MAX_PEERS]: number of steps this
+  // rank has completed (the epoch base, never rewound -- unlike the Adam step counter, which graph capture restores);
+  // [CACTO_MAX_PEERS + 1]: CTA ticket of the running launch
+  unsigned* mine = R.flags[R.rank];
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(mine + CACTO_MAX_PEERS) + 1u;
+  if (blockIdx.x == 0 && threadIdx.x < R.world) {          // the preceding gradient kernel has completed (stream order)
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(R.flags[threadIdx.x] + R.rank), "r"(epoch) : "memory");
+  }
+  if (threadIdx.x < R.world) {
+    const unsigned* f = mine + threadIdx.x;
+    unsigned seen = 0, spins = 0;
+    unsigned long long t0 = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+      if ((int)(seen - epoch) >= 0) break;
+      if ((++spins & 255u) == 0) {                         // a peer that never arrives: fail loudly after 20 s instead of hanging
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) __trap();
       }
     }
-    pT[j] = pi;
+  }
+  __syncthreads();
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = i0; j < n_other; j += stride) zero_other[j] = 0.f;
+  const float alpha = __ldg(alpha_dev);
+  for (int64_t i = i0; i < n; i += stride) {
+    float x[CACTO_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < CACTO_MAX_PEERS; ++r) {            // all peer loads in flight together (one NVLink round trip), ...
+      x[r] = 0.f;
+      if (r < R.world) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x[r]) : "l"(R.grad[r] + i) : "memory");
+    }
+    float gi = x[0];
+#pragma unroll
+    for (int r = 1; r < CACTO_MAX_PEERS; ++r)              // ... summed in rank order
+      if (r < R.world) gi += x[r];
+    adam_element(i, gi, p, m, v, alpha, omb1, omb2, eps, target, tau, pT, T);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                                  // the last CTA to finish advances the epoch base for the next launch
+    const unsigned ticket = atomicAdd(mine + CACTO_MAX_PEERS + 1, 1u);
+    if (ticket == gridDim.x - 1) {
+      mine[CACTO_MAX_PEERS + 1] = 0u;
+      *reinterpret_cast<volatile unsigned*>(mine + CACTO_MAX_PEERS) = epoch;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) k_transpose(const float* __restrict__ p, float* __restrict__ pT, LayerTable T, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int64_t j = i;
-  for (int l = 0; l < T.n; ++l) {
-    const int64_t sz = (int64_t)T.in[l] * T.out[l];
-    if (i >= T.W[l] && i < T.W[l] + sz) {
-      const int64_t e = i - T.W[l];
-      const int r = (int)(e / T.out[l]), c = (int)(e - (int64_t)r * T.out[l]);
-      j = T.W[l] + (int64_t)c * T.in[l] + r;
-      break;
-    }
-  }
-  pT[j] = p[i];
+  pT[transposed_index(T, i)] = p[i];
 }
 
 static LayerTable make_table(int is_critic, int ns, int na, int64_t* total) {
@@ -915,6 +983,38 @@ extern "C" int cacto_adam_step(float* params, float* grad, float* m, float* v, f
   }
   k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, m, v, alpha_t, alpha_dev_or_null, 1.f - beta1, 1.f - beta2, eps,
                                                                        target_or_null, tau, params_T_or_null, T, n);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cacto_adam_step_peer(float* params, const float* const* peer_grads, uint32_t* const* peer_flags, int32_t world, int32_t rank,
+                                    float* zero_other_or_null, int64_t n_other, float* m, float* v,
+                                    const float* alpha_dev, float beta1, float beta2, float eps, float* target_or_null, float tau,
+                                    float* params_T_or_null, int32_t is_critic, int32_t ns, int32_t na, int64_t n, int32_t max_ctas,
+                                    void* stream) {
+  if (max_ctas < 0) return CACTO_E_ARG;
+  if (!params || !peer_grads || !peer_flags || !m || !v || !alpha_dev) return CACTO_E_ARG;
+  if (world < 1 || world > CACTO_MAX_PEERS || rank < 0 || rank >= world || n_other < 0 || (n_other > 0 && !zero_other_or_null)) return CACTO_E_ARG;
+  int64_t total = 0;
+  LayerTable T = make_table(is_critic, ns, na, &total);
+  if (params_T_or_null == nullptr) {
+    if (n <= 0) return CACTO_E_SIZE;
+    T.n = 0;
+  } else if (n != total) {
+    return CACTO_E_SIZE;
+  }
+  PeerTable R;
+  R.world = world;
+  R.rank = rank;
+  for (int r = 0; r < CACTO_MAX_PEERS; ++r) {
+    R.grad[r] = r < world ? peer_grads[r] : nullptr;
+    R.flags[r] = r < world ? reinterpret_cast<unsigned*>(peer_flags[r]) : nullptr;
+    if (r < world && (!R.grad[r] || !R.flags[r])) return CACTO_E_ARG;
+  }
+  int64_t ctas = (n + 255) / 256;
+  if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
+  k_adam_peer<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(params, R, zero_other_or_null, n_other, m, v, alpha_dev, 1.f - beta1,
+                                                                            1.f - beta2, eps, target_or_null, tau, params_T_or_null, T, n);
   CACTO_LAUNCH_CHECK();
   return 0;
 }

@@ -64,16 +64,28 @@ class Adam:
         check(lib.cacto_adam_schedule(ptr(d['step']), ptr(d['boundaries']), ptr(d['values']), d['nb'], self.beta_1, self.beta_2,
                                       ptr(d['alpha']), ptr(zero), stream_ptr()), 'adam_schedule')
 
-    def step(self, net, target=None, tau=0.0, prepared=False):
+    def step(self, net, target=None, tau=0.0, prepared=False, peer=None, zero_other=None):
         """One Adam step on ``net`` from ``net.grad`` (zeroed afterwards); optionally the Polyak update
-        ``target = tau * net + (1 - tau) * target`` (RL.py:113-118) in the same launch."""
+        ``target = tau * net + (1 - tau) * target`` (RL.py:113-118) in the same launch.
+
+        ``peer`` = ``PeerReduce.table(net)`` switches to the data-parallel kernel: the gradient blocks of all ranks are summed
+        over NVLink inside the launch (no all-reduce before it); ``net.grad`` is then left as is and ``zero_other`` -- the
+        gradient block of the network stepped before this one -- is cleared instead (include/cacto_b200.h)."""
         m, v = self.moments(net)
         if not prepared:
             self.prepare(net.params.device)
         d = self._device_state(net.params.device)
-        check(lib.cacto_adam_step(ptr(net.params), ptr(net.grad), ptr(m), ptr(v), 0.0, ptr(d['alpha']), self.beta_1, self.beta_2,
-                                  self.epsilon, ptr(target.params if target is not None else None), float(tau), ptr(net.params_T),
-                                  net.is_critic, net.ns, net.na, net.n, stream_ptr()), 'adam_step')
+        tgt = ptr(target.params if target is not None else None)
+        if peer is not None:
+            grads, flags, rank, max_ctas = peer
+            check(lib.cacto_adam_step_peer(ptr(net.params), grads, flags, len(grads), rank, ptr(zero_other),
+                                           zero_other.numel() if zero_other is not None else 0, ptr(m), ptr(v), ptr(d['alpha']), self.beta_1,
+                                           self.beta_2, self.epsilon, tgt, float(tau), ptr(net.params_T), net.is_critic, net.ns, net.na, net.n,
+                                           max_ctas, stream_ptr()), 'adam_step_peer')
+        else:
+            check(lib.cacto_adam_step(ptr(net.params), ptr(net.grad), ptr(m), ptr(v), 0.0, ptr(d['alpha']), self.beta_1, self.beta_2,
+                                      self.epsilon, tgt, float(tau), ptr(net.params_T), net.is_critic, net.ns, net.na, net.n, stream_ptr()),
+                  'adam_step')
         self.iterations += 1
 
     def apply_gradients(self, grads_and_vars):

@@ -31,3 +31,115 @@ def global_batch(local_batch, dist):
     if dist is None or not dist.is_initialized():
         return int(local_batch)
     return int(local_batch) * dist.get_world_size()
+
+
+# ------------------------------------------------------------------------------------------ NVLink peer memory
+class PeerRegion:
+    """One zero-filled cudaMalloc block per rank that every rank of the box has mapped (``cacto_peer_*`` of
+    include/cacto_b200.h): ``bases[r]`` is the address of rank r's block in THIS process.  Built either across
+    processes (``exchange``: CUDA-IPC handles travel through ``dist.all_gather_object``) or inside one process
+    (``local_group``: the blocks of all simulated ranks on the current device -- what the single-GPU test uses)."""
+
+    def __init__(self, nbytes, rank, world, bases, owned, opened):
+        self.nbytes, self.rank, self.world, self.bases = int(nbytes), int(rank), int(world), list(bases)
+        self._owned, self._opened = owned, opened
+
+    @staticmethod
+    def _alloc(nbytes):
+        import ctypes as C
+        from ._lib import check, lib
+        p = C.c_void_p()
+        check(lib.cacto_peer_alloc(int(nbytes), C.byref(p)), 'peer_alloc')
+        return p.value
+
+    @classmethod
+    def exchange(cls, nbytes, dist):
+        import ctypes as C
+        from ._lib import check, lib
+        rank, world = dist.get_rank(), dist.get_world_size()
+        base = cls._alloc(nbytes)
+        handle = C.create_string_buffer(64)
+        check(lib.cacto_peer_export(C.c_void_p(base), handle), 'peer_export')
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        bases, opened = [], []
+        for r, h in enumerate(handles):
+            if r == rank:
+                bases.append(base)
+                continue
+            q = C.c_void_p()
+            check(lib.cacto_peer_open(C.create_string_buffer(h, 64), C.byref(q)), 'peer_open (rank %d)' % r)
+            bases.append(q.value)
+            opened.append(q.value)
+        dist.barrier()
+        return cls(nbytes, rank, world, bases, base, opened)
+
+    @classmethod
+    def local_group(cls, nbytes, world):
+        bases = [cls._alloc(nbytes) for _ in range(world)]
+        return [cls(nbytes, r, world, bases, bases[r], []) for r in range(world)]
+
+    def tensor(self, offset, count, dtype, device):
+        """Zero-copy torch view of ``count`` elements at byte ``offset`` of this rank's own block."""
+        import numpy as np
+        import torch
+        np_dt = np.dtype({torch.float32: 'f4', torch.int32: 'i4', torch.uint8: 'u1'}[dtype])
+        assert offset + count * np_dt.itemsize <= self.nbytes
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = dict(shape=(int(count),), typestr=np_dt.str, data=(self.bases[self.rank] + int(offset), False),
+                                          version=2, strides=None)
+        v._keepalive = self
+        t = torch.as_tensor(v, device=device)
+        assert t.data_ptr() == self.bases[self.rank] + int(offset)
+        return t
+
+    def close(self):
+        import ctypes as C
+        from ._lib import lib
+        for q in self._opened:
+            lib.cacto_peer_close(C.c_void_p(q))
+        self._opened = []
+        if self._owned:
+            lib.cacto_peer_free(C.c_void_p(self._owned))
+            self._owned = None
+
+
+class PeerReduce:
+    """Gradient exchange of the data-parallel update without a collective launch: the gradient blocks of the critic and
+    the actor and two rows of arrival words live in a ``PeerRegion``; ``table(net)`` gives the per-rank pointer arrays that
+    ``cacto_adam_step_peer`` (update.cu: k_adam_peer) sums over NVLink inside the Adam kernel.  Layout of every rank's
+    block (identical on all ranks): [critic flags 128 B][actor flags 128 B][critic grad][actor grad], 128-byte aligned.
+    ``max_ctas`` bounds the CTAs of the kernel (0 = no bound); only ranks simulated on ONE device need it (the CTAs spin while
+    they wait for the peers, and an SM full of spinning CTAs cannot be re-carved for the 200 KB gradient kernels)."""
+
+    MAX_PEERS = 8
+
+    @staticmethod
+    def region_bytes(n_critic, n_actor):
+        r = lambda b: (b + 127) // 128 * 128
+        return 256 + r(4 * n_critic) + r(4 * n_actor)
+
+    def __init__(self, region, critic, actor, max_ctas=0):
+        import ctypes as C
+        import torch
+        if region.world > self.MAX_PEERS:
+            raise ValueError('peer reduce supports up to %d GPUs of one box' % self.MAX_PEERS)
+        assert region.nbytes >= self.region_bytes(critic.n, actor.n)
+        self.region, self.rank, self.world = region, region.rank, region.world
+        r = lambda b: (b + 127) // 128 * 128
+        off = {id(critic): (0, 256), id(actor): (128, 256 + r(4 * critic.n))}
+        self._tables = {}
+        for net in (critic, actor):
+            f_off, g_off = off[id(net)]
+            grad = region.tensor(g_off, net.n, torch.float32, net.params.device)
+            net.grad = grad                                  # the kernels accumulate straight into the shared block
+            net._grad_views = net._make_views(grad)
+            grads = (C.c_void_p * region.world)(*[b + g_off for b in region.bases])
+            flags = (C.c_void_p * region.world)(*[b + f_off for b in region.bases])
+            self._tables[id(net)] = (grads, flags, region.rank, int(max_ctas))
+
+    def table(self, net):
+        return self._tables[id(net)]

@@ -40,6 +40,8 @@ enum cacto_system {
 #define CACTO_MAX_NS 13
 #define CACTO_MAX_NA 6
 #define CACTO_MAX_JOINTS 6
+#define CACTO_MAX_PEERS 8          /* GPUs of one box that share gradient blocks over NVLink peer memory */
+#define CACTO_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
 
 /* Serial chain extracted from the URDF (what Pinocchio builds in conf_*.py: RobotWrapper.BuildFromURDF). */
 typedef struct {
@@ -181,6 +183,15 @@ int cacto_actor_grad_generic(const cacto_sys_params* p, const cacto_mlp_desc* d_
                              const float* state_next, const float* Fu, const float* dr_da, float inv_B, float* grad, int64_t B,
                              void* stream);
 
+/* ---- K1 as CTA pairs (tcgen05 cta_group::2): same contract and arithmetic as cacto_rollout_tc16; a cluster of two CTAs steps
+ *      256-rollout macro tiles with M = 256 MMAs, each CTA holding half of W2 resident in shared memory (no W2 streaming).
+ *      w2img: cacto_actor_tc16p_image_bytes() bytes laid out per CTA rank by cacto_actor_tc16p_prepare. */
+int64_t cacto_actor_tc16p_image_bytes(void);
+int cacto_actor_tc16p_prepare(const float* actor_params, int32_t ns, int32_t na, void* w2img, void* stream);
+int cacto_rollout_tc16p(const cacto_sys_params* p, const float* actor_params, const void* w2img, const double* ics,
+                        const int32_t* horizon, int32_t T_max, double* states, double* controls, int32_t* flags,
+                        double* rewards, int64_t B, void* stream);
+
 /* ---- N4: NN.eval over a batch (NeuralNetwork.py:130-138): out[B][na] (actor) / out[B][1] (critic) */
 int cacto_actor_forward(const cacto_sys_params* p, const float* actor_params, const float* state, float* out,
                         int64_t B, void* stream);
@@ -218,6 +229,32 @@ int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_
  * RL.py:82-85; nb = 0 for a constant rate values[0]), increments the counter and clears zero_or_null[0]. */
 int cacto_adam_schedule(int64_t* step, const float* boundaries, const float* values, int32_t nb, float beta1,
                         float beta2, float* alpha_out, float* zero_or_null, void* stream);
+
+/* ---- Data-parallel update (the reference is single-GPU, main.py:59): cacto_adam_step with the gradient
+ *      all-reduce fused in over NVLink peer memory.  peer_grads[r] / peer_flags[r] (HOST arrays of `world` device pointers)
+ *      are rank r's gradient block of this network (n floats) and its flag row (32 zero-initialised uint32: CACTO_MAX_PEERS
+ *      arrival words, a launch counter, a CTA ticket), both inside regions obtained from cacto_peer_alloc and mapped with
+ *      cacto_peer_open; entry [rank] is the caller's own.  Every rank must issue the same sequence of calls.  The kernel
+ *      announces its launch number to every peer, waits for all of them, sums the
+ *      blocks in rank order (bit-identical replicas) and applies the step.  It does NOT clear the caller's gradient block
+ *      (peers may still read it); it clears zero_other_or_null[0..n_other), the block of the network whose step precedes
+ *      this one (critic and actor steps alternate, RL.py:104-109).  max_ctas > 0 bounds the CTAs of the launch (grid-stride
+ *      over the parameters; 0 = one thread per parameter): the CTAs spin while they wait, which matters only when several
+ *      ranks share one device, as the single-GPU test does.  Traps after 20 s if a peer never arrives. */
+int cacto_adam_step_peer(float* params, const float* const* peer_grads, uint32_t* const* peer_flags, int32_t world,
+                         int32_t rank, float* zero_other_or_null, int64_t n_other, float* m,
+                         float* v, const float* alpha_dev, float beta1, float beta2, float eps, float* target_or_null,
+                         float tau, float* params_T_or_null, int32_t is_critic, int32_t ns, int32_t na, int64_t n,
+                         int32_t max_ctas, void* stream);
+
+/* Peer-memory regions: cudaMalloc'ed (zero-filled) blocks that other processes of the box map through CUDA IPC.
+ * export writes CACTO_IPC_HANDLE_BYTES bytes; open maps a handle received from another process (peer access over
+ * NVLink is enabled lazily) and close unmaps it.  Host-synchronous; not for use inside stream capture. */
+int cacto_peer_alloc(int64_t bytes, void** dev_ptr_out);
+int cacto_peer_free(void* dev_ptr);
+int cacto_peer_export(void* dev_ptr, void* handle_out);
+int cacto_peer_open(const void* handle, void** dev_ptr_out);
+int cacto_peer_close(void* dev_ptr);
 
 /* Rebuild the per-layer transposed copy of a parameter block (W^T per layer, biases copied). */
 int cacto_transpose_params(const float* params, float* params_T, int32_t is_critic, int32_t ns, int32_t na,

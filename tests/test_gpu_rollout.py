@@ -83,7 +83,7 @@ def test_create_TO_init_matches_reference_goldens(system):
             assert np.abs(ct - ref_c).max() <= tol * max(1.0, np.abs(ref_c).max())
 
 
-@pytest.mark.parametrize('engine,B', [('tc', 1000), ('tf32', 1000), ('tc', 40000)])
+@pytest.mark.parametrize('engine,B', [('tc', 1000), ('tf32', 1000), ('tc', 40000), ('tc2', 1000), ('tc2', 40000)])
 def test_tensor_core_engine_agrees_with_fma_engine(engine, B):
     """Full-size tile coverage: manipulator rollouts with mixed horizons, tensor-core engine vs fp32 FMA engine, same actor.
     B = 40000 gives the persistent 'tc' kernel 313 tiles over 148 CTAs (2-3 tiles per CTA, ragged last tile)."""
