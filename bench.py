@@ -257,7 +257,7 @@ def run_b200(args):
     h2d = ics_host.numel() * 8 + B * 4
     d2h = (st_host.numel() + ct_host.numel()) * 8 + fl_host.numel() * 4
 
-    # ---- K3 updates/s (secondary metric): conf batch per GPU, data resident, gradients all-reduced over NCCL
+    # ---- K3 updates/s (secondary metric): conf batch per GPU, data resident, gradients summed across GPUs inside the Adam kernels
     Bu = conf.BATCH_SIZE
     g = torch.Generator(device='cpu').manual_seed(rank)
     lo, hi = torch.as_tensor(conf.x_init_min), torch.as_tensor(conf.x_init_max)
@@ -282,26 +282,30 @@ def run_b200(args):
     b.record(stream)
     torch.cuda.synchronize()
     updates_per_s = n_up / (max_over_ranks(a.elapsed_time(b)) * 1e-3)
-    # the same update replayed as a CUDA graph (6 kernel nodes)
-    graph_updates_per_s = None
-    if world == 1:               # a capture failure on one rank would leave the others blocked in the all-reduce
+    # the same update replayed as a CUDA graph (6 kernel nodes; data-parallel: the gradient exchange happens inside the two
+    # Adam nodes over NVLink peer memory, so the graph holds no collective)
+    graph_updates_per_s, n_gr = None, 1000
+    if world == 1 or rl._peer is not None:
         try:
             ug = rl.make_update_graph(Bu)
             for k_, t_ in (('state', s), ('state_next', sn), ('partial_rtg', pr), ('dVdx', dv), ('done', d), ('term', term), ('weights', w)):
                 ug.io[k_].copy_(t_)
             for _ in range(20):
                 ug.replay()
-            torch.cuda.synchronize()
-            n_gr = 1000
+            barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             for _ in range(n_gr):
                 ug.replay()
             b.record(stream)
             torch.cuda.synchronize()
-            graph_updates_per_s = n_gr / (a.elapsed_time(b) * 1e-3)
+            graph_ms = a.elapsed_time(b)
+            del ug
         except Exception as exc:           # report, do not hide
-            graph_updates_per_s = f'failed: {type(exc).__name__}: {exc}'
+            graph_ms, graph_updates_per_s = -1.0, f'failed: {type(exc).__name__}: {exc}'
+        graph_ms_all = max_over_ranks(graph_ms)
+        if graph_ms > 0:
+            graph_updates_per_s = n_gr / (graph_ms_all * 1e-3)
     # the update at the batch sizes of BASELINE configs 2 / 3 (PER batch 4096, critic batch 16384), single GPU, eager launches
     large_batch = {}
     if world == 1:
@@ -375,6 +379,9 @@ def run_b200(args):
             'clocks': clocks,
             'extra': {'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s,
                       'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world, 'update_kernels_per_update': 6,
+                      'update_gradient_exchange': ('none (1 GPU)' if world == 1 else
+                                                   'NVLink peer-memory sum inside the Adam kernels (k_adam_peer)' if rl._peer is not None else
+                                                   'NCCL all-reduce per network'),
                       'fp32_fma_peak_tflops_measured': fma_peak_tflops, 'sobolev_update_large_batch': large_batch},
         }
         if cpu is not None:
