@@ -16,10 +16,27 @@ namespace cacto {
 __host__ __device__ constexpr int pad_odd(int w) { return (w & 1) ? w : w + 1; }
 
 // Rows [row0, row0+rows) of a row-major [B][W] array  <->  a shared tile with stride pad_odd(W).
-// Global accesses are fully coalesced (consecutive threads touch consecutive elements).
+// Global accesses are fully coalesced (consecutive threads touch consecutive elements).  With an odd W the tile is the
+// row block itself (stride W): it moves as 16-byte vectors without any index arithmetic -- the div/mod per element of the
+// general path was most of the instruction count of the dynamics-step kernel (profiles/README.md).
+template <typename T>
+__device__ __forceinline__ bool vec16_ok(const void* g, int count) {
+  return (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (count * (int)sizeof(T)) % 16 == 0;
+}
 template <int W, int NT, typename T>
 __device__ __forceinline__ void tile_load_rows(const T* __restrict__ g, T* __restrict__ s, int rows) {
   constexpr int WP = pad_odd(W);
+  if (WP == W) {
+    const int count = rows * W;
+    if (vec16_ok<T>(g, count)) {
+      const int4* g4 = reinterpret_cast<const int4*>(g);
+      int4* s4 = reinterpret_cast<int4*>(s);
+      for (int i = threadIdx.x; i < count * (int)sizeof(T) / 16; i += NT) s4[i] = g4[i];
+    } else {
+      for (int i = threadIdx.x; i < count; i += NT) s[i] = g[i];
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < rows * W; i += NT) {
     int r = i / W, c = i - r * W;
     s[r * WP + c] = g[i];
@@ -28,6 +45,17 @@ __device__ __forceinline__ void tile_load_rows(const T* __restrict__ g, T* __res
 template <int W, int NT, typename T>
 __device__ __forceinline__ void tile_store_rows(T* __restrict__ g, const T* __restrict__ s, int rows) {
   constexpr int WP = pad_odd(W);
+  if (WP == W) {
+    const int count = rows * W;
+    if (vec16_ok<T>(g, count)) {
+      int4* g4 = reinterpret_cast<int4*>(g);
+      const int4* s4 = reinterpret_cast<const int4*>(s);
+      for (int i = threadIdx.x; i < count * (int)sizeof(T) / 16; i += NT) g4[i] = s4[i];
+    } else {
+      for (int i = threadIdx.x; i < count; i += NT) g[i] = s[i];
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < rows * W; i += NT) {
     int r = i / W, c = i - r * W;
     g[i] = s[r * WP + c];

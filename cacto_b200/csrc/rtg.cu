@@ -1,5 +1,6 @@
 // rtg.cu -- K5: n-step reward-to-go windows of RL_AC.RL_Solve (RL.py:173-187) for a ragged batch of
-// TO trajectories.  One CTA per trajectory, one thread per knot; rewards staged in shared memory.
+// TO trajectories.  One CTA per trajectory, one thread per knot; rewards staged in shared memory; the s_next block is
+// written as one coalesced shifted copy of the state block.
 // Bit-exact with the reference: each window is summed left-to-right in fp64 starting from 0
 // (Python's builtin sum), then rounded to float32 and stored back as fp64 (quirk Q12).  There is no
 // discount factor in the reference (gamma == 1).
@@ -43,16 +44,18 @@ __global__ void __launch_bounds__(RTG_THREADS) k_rtg_window(const int64_t* __res
     for (int k = final_step + 1; k <= T; ++k) acc = __dadd_rn(acc, r[k]);
     partial[o + i] = part;
     total[o + i] = (double)(float)acc;
+    if (i == 0) ep_return[e] = acc;                 // the same left-to-right sum over all knots, unrounded
     done[o + i] = d;
     term[o + i] = (i == T) ? 1.0 : 0.0;
-    const bool copy = (d == 0.0);
-    for (int c = 0; c < ns; ++c) s_next[(o + i) * ns + c] = copy ? states[(o + final_step + 1) * ns + c] : 0.0;
   }
-  if (threadIdx.x == 0) {
-    double acc = 0.0;
-    for (int k = 0; k < K; ++k) acc = __dadd_rn(acc, r[k]);
-    ep_return[e] = acc;
-  }
+  // s_next[i] = state[final_step + 1] where the window ends before the trajectory does (done == 0), else 0 (RL.py:180-184):
+  // rows i < T - n are a copy of the state block shifted by n + 1 knots, so the CTA moves it as one contiguous, fully
+  // coalesced stream instead of ns strided stores per knot
+  const int n_copy = mc ? 0 : max(0, T - nsteps_td);        // knots with i + n < T
+  const int64_t shift = (int64_t)(nsteps_td + 1) * ns;
+  const double* src = states + o * ns;
+  double* dst = s_next + o * ns;
+  for (int j = threadIdx.x; j < K * ns; j += RTG_THREADS) dst[j] = (j < n_copy * ns) ? src[j + shift] : 0.0;
 }
 
 }  // namespace cacto
@@ -65,7 +68,7 @@ extern "C" int cacto_rtg_window(const int64_t* offsets, int32_t E, const double*
   if (!offsets || !rwrd || !states || !partial || !total_rtg || !s_next || !done || !term || !ep_return) return CACTO_E_ARG;
   if (E < 0 || ns < 1 || nsteps_td < 0) return CACTO_E_SIZE;
   if (E == 0) return 0;
-  const int smem_knots = 4096;             // 32 KB of rewards; longer trajectories read global memory
+  const int smem_knots = 512;              // 4 KB of rewards (every conf has <= 501 knots) so that 16 CTAs fit an SM; longer trajectories read global memory
   k_rtg_window<<<E, RTG_THREADS, smem_knots * sizeof(double), (cudaStream_t)stream>>>(
       offsets, rwrd, states, ns, nsteps_td, mc, partial, total_rtg, s_next, done, term, ep_return, smem_knots);
   CACTO_LAUNCH_CHECK();

@@ -79,3 +79,25 @@ def test_rl_solve_env_rl_resimulates_the_controls():
     np.testing.assert_array_equal(got[2], total)
     np.testing.assert_array_equal(got[3], snext)
     np.testing.assert_array_equal(got[4], done)
+
+
+@pytest.mark.parametrize('mc', [0, 1])
+def test_long_trajectories_and_mc(mc):
+    """Car-sized trajectories (501 knots, n = 125: the shared-memory staging limit of 512 knots), one beyond it (rewards read from
+    global memory), windows longer than the trajectory, and MC mode (window = whole trajectory, nothing copied into s_next)."""
+    from cacto_b200.rtg import rtg_batch
+    rng = np.random.default_rng(3)
+    conf = SimpleNamespace(nb_state=6, MC=mc, nsteps_TD_N=125)
+    lens = [500, 511, 512, 700, 3, 125, 126]
+    states = [rng.normal(size=(T + 1, 6)) for T in lens]
+    costs = [rng.uniform(0, 2, T + 1) * 10.0 ** rng.integers(-5, 1, T + 1) for T in lens]
+    out = rtg_batch(conf, states, costs)
+    off = out['offsets']
+    for e in range(len(lens)):
+        _, partial, total, snext, done, rwrd, term, ret = ortg.rl_solve(conf, states[e], costs[e])
+        sl = slice(off[e], off[e + 1])
+        np.testing.assert_array_equal(out['partial'][sl].cpu().numpy(), partial)
+        np.testing.assert_array_equal(out['total'][sl].cpu().numpy(), total)
+        np.testing.assert_array_equal(out['state_next'][sl].cpu().numpy(), snext)
+        np.testing.assert_array_equal(out['done'][sl].cpu().numpy(), done)
+        assert float(out['ep_return'][e]) == ret
