@@ -19,7 +19,7 @@ import torch
 from ._lib import check, lib, ptr, stream_ptr
 from .environment import _as_cuda, _device
 from .optim import Adam, PiecewiseConstantDecay
-from .parallel import PeerReduce, PeerRegion, allreduce_sum
+from .parallel import PeerReduce, PeerRegion, PeerUnavailable, allreduce_sum
 from .rtg import rtg_batch as _rtg_batch
 
 
@@ -91,8 +91,13 @@ class RL_AC:
             if self.reduce == 'peer' and self.dist.get_world_size() > 1 and self.actor_model.params.is_cuda:
                 region = self._peer_region
                 if region is None:
-                    region = PeerRegion.exchange(PeerReduce.region_bytes(self.critic_model.n, self.actor_model.n), self.dist)
-                self._peer = PeerReduce(region, self.critic_model, self.actor_model, max_ctas=self._peer_max_ctas)
+                    try:
+                        region = PeerRegion.exchange(PeerReduce.region_bytes(self.critic_model.n, self.actor_model.n), self.dist)
+                    except PeerUnavailable as e:         # unanimous across ranks: every rank takes the NCCL all-reduce instead
+                        import warnings
+                        warnings.warn('peer-memory gradient exchange unavailable (%s): using NCCL all-reduce' % e)
+                if region is not None:
+                    self._peer = PeerReduce(region, self.critic_model, self.actor_model, max_ctas=self._peer_max_ctas)
 
     # ------------------------------------------------------------------------------ update
     def _reduce_and_step(self, opt, net, other, target=None, tau=0.0, prepared=False):

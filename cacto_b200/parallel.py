@@ -34,6 +34,10 @@ def global_batch(local_batch, dist):
 
 
 # ------------------------------------------------------------------------------------------ NVLink peer memory
+class PeerUnavailable(RuntimeError):
+    """The GPUs / processes of this job cannot share memory through CUDA IPC (raised on every rank alike)."""
+
+
 class PeerRegion:
     """One zero-filled cudaMalloc block per rank that every rank of the box has mapped (``cacto_peer_*`` of
     include/cacto_b200.h): ``bases[r]`` is the address of rank r's block in THIS process.  Built either across
@@ -54,25 +58,48 @@ class PeerRegion:
 
     @classmethod
     def exchange(cls, nbytes, dist):
+        """Collective over ``dist``.  Every rank allocates and exports its block, the handles travel through
+        ``all_gather_object``, every rank maps the others, and a final MIN all-reduce makes the outcome unanimous: if any
+        rank could not export or map (IPC not permitted between the processes, no peer access between two GPUs), ALL ranks
+        release what they hold and raise ``PeerUnavailable`` -- no rank is left waiting for a peer that gave up."""
         import ctypes as C
-        from ._lib import check, lib
+        import torch
+        from ._lib import lib
         rank, world = dist.get_rank(), dist.get_world_size()
-        base = cls._alloc(nbytes)
-        handle = C.create_string_buffer(64)
-        check(lib.cacto_peer_export(C.c_void_p(base), handle), 'peer_export')
+        base, handle, err = None, None, None
+        try:
+            base = cls._alloc(nbytes)
+            buf = C.create_string_buffer(64)
+            rc = lib.cacto_peer_export(C.c_void_p(base), buf)
+            if rc != 0:
+                raise RuntimeError('cacto_peer_export: CUDA error %d' % rc)
+            handle = bytes(buf.raw)
+        except RuntimeError as e:
+            err = e
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle.raw))
+        dist.all_gather_object(handles, handle)
         bases, opened = [], []
-        for r, h in enumerate(handles):
-            if r == rank:
-                bases.append(base)
-                continue
-            q = C.c_void_p()
-            check(lib.cacto_peer_open(C.create_string_buffer(h, 64), C.byref(q)), 'peer_open (rank %d)' % r)
-            bases.append(q.value)
-            opened.append(q.value)
-        dist.barrier()
-        return cls(nbytes, rank, world, bases, base, opened)
+        if err is None and all(h is not None for h in handles):
+            for r, h in enumerate(handles):
+                if r == rank:
+                    bases.append(base)
+                    continue
+                q = C.c_void_p()
+                rc = lib.cacto_peer_open(C.create_string_buffer(h, 64), C.byref(q))
+                if rc != 0:
+                    err = RuntimeError('cacto_peer_open (rank %d): CUDA error %d' % (r, rc))
+                    break
+                bases.append(q.value)
+                opened.append(q.value)
+        elif err is None:
+            err = RuntimeError('a peer could not export its block')
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=torch.device('cuda', torch.cuda.current_device()))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        region = cls(nbytes, rank, world, bases, base, opened)
+        if int(ok[0]) == 0:
+            region.close()
+            raise PeerUnavailable(str(err) if err is not None else 'another rank could not map the peer blocks')
+        return region
 
     @classmethod
     def local_group(cls, nbytes, world):
