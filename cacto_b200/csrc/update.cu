@@ -841,9 +841,11 @@ static int smem_attr(K k, size_t bytes) {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-// samples per CTA: 16 when the batch fills the GPU with 16-sample tiles, 4 at the reference's batch sizes (64 / 128: a latency
-// chain of ~25 dependent phases per CTA -- fewer rows per CTA shorten every phase and occupy more SMs), else 8
-static int pick_tile(int64_t B) { return B >= 16 * 148 ? 16 : (B <= 4 * 148 / 2 ? 4 : 8); }
+// Samples per CTA.  A CTA walks a latency chain of ~25 dependent phases whose length grows with its rows, and one CTA fits an SM
+// (200 KB of shared memory): the smallest tile that still covers the batch in ONE wave of 148 CTAs wins -- 2 rows up to B = 296
+// (the reference's 64 / 128: 103.7 / 109.4 us per update as a CUDA graph vs 127 us with 8-row tiles), 4 up to 592, 8 below the
+// size where 16-row tiles fill the GPU, 16 (best FMA : LDS ratio) beyond.
+static int pick_tile(int64_t B) { return B >= 16 * 148 ? 16 : (B <= 2 * 148 ? 2 : (B <= 4 * 148 ? 4 : 8)); }
 
 template <int SYS>
 static int launch_actor_grad(const cacto_sys_params& P, const float* aw, const float* awT, const float* cw, const float* cwT,
@@ -857,10 +859,14 @@ static int launch_actor_grad(const cacto_sys_params& P, const float* aw, const f
     auto k = k_actor_grad<SYS, 8>;
     if (int e = smem_attr(k, sizeof(ActorSmem<8>))) return e;
     k<<<(unsigned)((B + 7) / 8), UP_NT, sizeof(ActorSmem<8>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
-  } else {
+  } else if (pick_tile(B) == 4) {
     auto k = k_actor_grad<SYS, 4>;
     if (int e = smem_attr(k, sizeof(ActorSmem<4>))) return e;
     k<<<(unsigned)((B + 3) / 4), UP_NT, sizeof(ActorSmem<4>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
+  } else {
+    auto k = k_actor_grad<SYS, 2>;
+    if (int e = smem_attr(k, sizeof(ActorSmem<2>))) return e;
+    k<<<(unsigned)((B + 1) / 2), UP_NT, sizeof(ActorSmem<2>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
   }
   CACTO_LAUNCH_CHECK();
   return 0;
@@ -897,10 +903,16 @@ extern "C" int cacto_critic_grad(const cacto_sys_params* p, const float* critic_
     k<<<(unsigned)((B + 7) / 8), UP_NT, sizeof(CriticSmem<8>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
                                                                      state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
                                                                      V_target_s, loss, B);
-  } else {
+  } else if (pick_tile(B) == 4) {
     auto k = k_critic_grad<4>;
     if (int e = smem_attr(k, sizeof(CriticSmem<4>))) return e;
     k<<<(unsigned)((B + 3) / 4), UP_NT, sizeof(CriticSmem<4>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
+                                                                     state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
+                                                                     V_target_s, loss, B);
+  } else {
+    auto k = k_critic_grad<2>;
+    if (int e = smem_attr(k, sizeof(CriticSmem<2>))) return e;
+    k<<<(unsigned)((B + 1) / 2), UP_NT, sizeof(CriticSmem<2>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
                                                                      state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
                                                                      V_target_s, loss, B);
   }
