@@ -29,6 +29,24 @@ __host__ __device__ __forceinline__ constexpr int koff(int l) { return l == 0 ? 
 __device__ __forceinline__ float slog(float x) { return x > 0.f ? logf(fmaxf(x, 1e-7f) + 1.f) : -logf(fmaxf(-x, 1e-7f) + 1.f); }
 __device__ __forceinline__ float slog_grad(float x) { return fabsf(x) >= 1e-7f ? 1.f / (fabsf(x) + 1.f) : 0.f; }
 
+// sin / cos of the SIREN layers, deliberately NOT inlined: the accurate sinf / sincosf expand to ~40 instructions per call and
+// sat in ~100 epilogue call sites -- a third of the 13 k instructions of k_critic_grad, whose small-batch runs are bound by
+// instruction fetch (ncu: stall_no_inst 35 % of the samples at B = 64), every CTA walking the code once.
+__device__ __noinline__ float sin_call(float x) { return sinf(x); }
+__device__ __noinline__ float2 sincos_call(float x) {
+  float2 r;
+  sincosf(x, &r.x, &r.y);
+  return r;
+}
+__device__ __forceinline__ float4 sin4(float4 a, float4 b) {
+  return make_float4(sin_call(a.x + b.x), sin_call(a.y + b.y), sin_call(a.z + b.z), sin_call(a.w + b.w));
+}
+__device__ __forceinline__ void sincos4(float4 a, float4 b, float4& s, float4& c) {
+  const float2 x = sincos_call(a.x + b.x), y = sincos_call(a.y + b.y), z = sincos_call(a.z + b.z), w = sincos_call(a.w + b.w);
+  s = make_float4(x.x, y.x, z.x, w.x);
+  c = make_float4(x.y, y.y, z.y, w.y);
+}
+
 // Order in which the streamed (K % 4 == 0) weight matrices are consumed by a kernel; built by every
 // thread identically, read when a GEMM asks the pipeline to prefetch its successor.
 struct WeightSeq {
@@ -125,22 +143,22 @@ __device__ __forceinline__ void critic_forward_tile(WeightPipe& pipe, SM& sm, in
                                                     const float (*XN)[NSP], float* bufA, float* bufB, int ld, float* V) {
   tile_gemm<S, CR_H1, UP_NT, false>(&XN[0][0], NSP, L.ns, cp.W0, CR_H1, [&](int r, int c, const float4& a) {
     const float4 b = *reinterpret_cast<const float4*>(cp.b[0] + c);
-    *reinterpret_cast<float4*>(bufA + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
+    *reinterpret_cast<float4*>(bufA + r * ld + c) = sin4(a, b);
   });
   __syncthreads();
   streamed<S, CR_H2>(pipe, sm, gi, bufA, ld, CR_H1, [&](int r, int c, const float4& a) {
     const float4 b = *reinterpret_cast<const float4*>(cp.b[1] + c);
-    *reinterpret_cast<float4*>(bufB + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
+    *reinterpret_cast<float4*>(bufB + r * ld + c) = sin4(a, b);
   });
   __syncthreads();
   streamed<S, CR_H3>(pipe, sm, gi, bufB, ld, CR_H2, [&](int r, int c, const float4& a) {
     const float4 b = *reinterpret_cast<const float4*>(cp.b[2] + c);
-    *reinterpret_cast<float4*>(bufA + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
+    *reinterpret_cast<float4*>(bufA + r * ld + c) = sin4(a, b);
   });
   __syncthreads();
   streamed<S, CR_H4>(pipe, sm, gi, bufA, ld, CR_H3, [&](int r, int c, const float4& a) {
     const float4 b = *reinterpret_cast<const float4*>(cp.b[3] + c);
-    *reinterpret_cast<float4*>(bufB + r * ld + c) = make_float4(sinf(a.x + b.x), sinf(a.y + b.y), sinf(a.z + b.z), sinf(a.w + b.w));
+    *reinterpret_cast<float4*>(bufB + r * ld + c) = sin4(a, b);
   });
   __syncthreads();
   tile_gemm_small<S, UP_NT, 8, true>(bufB, ld, CR_H4, cp.W4, 1, 0, [&](int s, int, float v) { V[s] = v + cp.b[4][0]; });
@@ -222,10 +240,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
     return [&, l](int r, int c, const float4& a) {
       const float4 b = *reinterpret_cast<const float4*>(cp.b[l] + c);
       float4 s, co;
-      sincosf(a.x + b.x, &s.x, &co.x);
-      sincosf(a.y + b.y, &s.y, &co.y);
-      sincosf(a.z + b.z, &s.z, &co.z);
-      sincosf(a.w + b.w, &s.w, &co.w);
+      sincos4(a, b, s, co);
       *reinterpret_cast<float4*>(&sm.SN[r][koff(l) + c]) = s;
       *reinterpret_cast<float4*>(&sm.CS[r][koff(l) + c]) = co;
     };
@@ -490,10 +505,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
     return [&, l, out](int r, int c, const float4& a) {
       const float4 b = *reinterpret_cast<const float4*>(cp.b[l] + c);
       float4 s, co;
-      sincosf(a.x + b.x, &s.x, &co.x);
-      sincosf(a.y + b.y, &s.y, &co.y);
-      sincosf(a.z + b.z, &s.z, &co.z);
-      sincosf(a.w + b.w, &s.w, &co.w);
+      sincos4(a, b, s, co);
       *reinterpret_cast<float4*>(out + r * CR_H4 + c) = s;
       *reinterpret_cast<float4*>(&sm.CS[r][koff(l) + c]) = co;
     };
@@ -650,10 +662,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_forward(const __grid_constant_
     return [&, l, out](int r, int c, const float4& a) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(cw + L.b[l] + c));
       float4 s, co;
-      sincosf(a.x + b.x, &s.x, &co.x);
-      sincosf(a.y + b.y, &s.y, &co.y);
-      sincosf(a.z + b.z, &s.z, &co.z);
-      sincosf(a.w + b.w, &s.w, &co.w);
+      sincos4(a, b, s, co);
       *reinterpret_cast<float4*>(out + r * ACTOR_H + c) = s;
       *reinterpret_cast<float4*>(&sm.CS[r][koff(l) + c]) = co;
     };
@@ -889,7 +898,7 @@ extern "C" int cacto_critic_grad(const cacto_sys_params* p, const float* critic_
     return CACTO_E_ARG;
   if (!mc && (!state_next || !done)) return CACTO_E_ARG;
   if (w_S != 0.f && !dVdx) return CACTO_E_ARG;
-  if (!aligned16(critic_params) || !aligned16(critic_params_T) || !aligned16(target_params)) return CACTO_E_ALIGN;
+  if (!aligned16(critic_params) || !aligned16(critic_params_T) || !aligned16(target_params) || !aligned16(grad)) return CACTO_E_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   if (pick_tile(B) == 16) {
     auto k = k_critic_grad<16>;
@@ -927,7 +936,8 @@ extern "C" int cacto_actor_grad(const cacto_sys_params* p, const float* actor_pa
   if (B < 0) return CACTO_E_SIZE;
   if (B == 0) return 0;
   if (!actor_params || !actor_params_T || !critic_params || !critic_params_T || !state || !term || !grad) return CACTO_E_ARG;
-  if (!aligned16(actor_params) || !aligned16(actor_params_T) || !aligned16(critic_params) || !aligned16(critic_params_T)) return CACTO_E_ALIGN;
+  if (!aligned16(actor_params) || !aligned16(actor_params_T) || !aligned16(critic_params) || !aligned16(critic_params_T) || !aligned16(grad))
+    return CACTO_E_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   switch (p->system) {
     case CACTO_SINGLE_INTEGRATOR: return launch_actor_grad<CACTO_SINGLE_INTEGRATOR>(*p, actor_params, actor_params_T, critic_params, critic_params_T, state, term, inv_B, grad, actions, B, st);
