@@ -153,6 +153,86 @@ struct WeightPipe {
 template <int N>
 __host__ __device__ constexpr int chunk_rows(int K) { return (W_CHUNK / N) < K ? (W_CHUNK / N) : K; }
 
+// Thread mapping of the streamed GEMMs for SMALL tiles (S <= 4, the reference's batch sizes): with one thread per (row group,
+// column group) a 2-row tile keeps 1 (N = 64) to 4 (N = 256) of the 8 warps busy on a dependent chain of K / 4 steps while the
+// rest wait at the barrier (ncu at B = 64: barrier = 36 % of the stall samples).  Here the reduction is split over the four
+// quarter-warps (lane = 8 kg + c8: k-group kg takes k = 16 j + 4 kg .. + 3 of every block of 16; the 8 lanes of a quarter own 8
+// adjacent float4 column groups: conflict-free 128-byte W reads, one broadcast float4 of A), rows over warps; the four partial
+// sums meet in a two-step shuffle butterfly and lane group kg runs the epilogue of row kg.  K % 16 == 0.  (For 8- and 16-row
+// tiles this mapping measured slower -- profiles/README.md -- the A broadcasts become the shared-memory bottleneck.)
+template <int S, int N, int NT>
+struct SplitKMap {
+  static_assert(N % 32 == 0, "N must be a multiple of 32");
+  static constexpr int CG = N / 4;              // float4 column groups
+  static constexpr int WARPS = NT / 32;
+  static constexpr int WC = CG / 8;             // warps across the columns
+  static_assert(WC <= WARPS && WARPS % WC == 0, "column warps must tile the CTA");
+  static constexpr int RG = (WARPS / WC) < S ? (WARPS / WC) : S;   // row groups in use (further warps idle)
+  static_assert(S % RG == 0, "rows must split evenly");
+  static constexpr int TM = S / RG;             // rows per thread
+  static_assert(TM <= 4, "the epilogue hands row r to lane group r");
+};
+
+template <int S, int N, int NT, typename Epi>
+__device__ __forceinline__ void gemm_streamed_splitk(WeightPipe& pipe, const float* __restrict__ A, int lda, int K,
+                                                     const float* __restrict__ Wg, const float* __restrict__ next, int next_floats,
+                                                     Epi&& epi) {
+  typedef SplitKMap<S, N, NT> M;
+  constexpr int TM = M::TM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kg = lane >> 3, cg = (warp % M::WC) * 8 + (lane & 7), rg = warp / M::WC;
+  const bool active = rg < M::RG;
+  float4 acc[TM];
+#pragma unroll
+  for (int r = 0; r < TM; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int rows_per_chunk = chunk_rows<N>(K);           // a multiple of 16 (8192 / N, or K)
+  const int nchunks = (K + rows_per_chunk - 1) / rows_per_chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int k0 = c * rows_per_chunk;
+    const int kc = min(rows_per_chunk, K - k0);
+    if (c + 1 < nchunks) {
+      const int kn = min(rows_per_chunk, K - (k0 + rows_per_chunk));
+      pipe.issue(Wg + (size_t)(k0 + rows_per_chunk) * N, kn * N);
+    } else {
+      pipe.issue(next, next_floats);
+    }
+    const float* w = pipe.wait();
+    if (active) {
+      const float* a0 = A + (size_t)(rg * TM) * lda + k0 + 4 * kg;
+      const float4* wp = reinterpret_cast<const float4*>(w) + (size_t)(4 * kg) * (N / 4) + cg;
+#pragma unroll 2
+      for (int kb = 0; kb < kc; kb += 16) {
+        const float4* wr = wp + (size_t)kb * (N / 4);
+        const float4 w0 = wr[0], w1 = wr[N / 4], w2 = wr[2 * (N / 4)], w3 = wr[3 * (N / 4)];
+#pragma unroll
+        for (int r = 0; r < TM; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(a0 + r * lda + kb);
+          fma4(acc[r], a.x, w0);
+          fma4(acc[r], a.y, w1);
+          fma4(acc[r], a.z, w2);
+          fma4(acc[r], a.w, w3);
+        }
+      }
+    }
+    __syncthreads();          // every thread is done with this slot before it is refilled
+  }
+  if (active) {               // warp-uniform: whole warps are active or idle
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      float4 v = acc[r];
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 8);
+      v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
+      v.z += __shfl_xor_sync(0xffffffffu, v.z, 8);
+      v.w += __shfl_xor_sync(0xffffffffu, v.w, 8);
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
+      v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+      v.z += __shfl_xor_sync(0xffffffffu, v.z, 16);
+      v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
+      if (r == kg) epi(rg * TM + r, 4 * cg, v);
+    }
+  }
+}
+
 // C = A * W with W [K x N] (row-major, ld = N, K % 4 == 0) streamed through the weight pipeline.
 // Contract: the first chunk of W is already in flight; while the last chunk is being consumed the first
 // chunk of `next` (next_floats floats, nullptr for none) is issued.  Ends WITHOUT a trailing barrier for
@@ -160,6 +240,10 @@ __host__ __device__ constexpr int chunk_rows(int K) { return (W_CHUNK / N) < K ?
 template <int S, int N, int NT, typename Epi>
 __device__ __forceinline__ void gemm_streamed(WeightPipe& pipe, const float* __restrict__ A, int lda, int K,
                                               const float* __restrict__ Wg, const float* __restrict__ next, int next_floats, Epi&& epi) {
+  if constexpr (S <= 4) {
+    gemm_streamed_splitk<S, N, NT>(pipe, A, lda, K, Wg, next, next_floats, epi);
+    return;
+  }
   typedef GemmMap<S, N, NT> M;
   constexpr int TM = M::TM;
   const int cg = threadIdx.x % M::CG, rg = threadIdx.x / M::CG;
