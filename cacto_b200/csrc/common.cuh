@@ -12,6 +12,32 @@ namespace cacto {
     if (e__ != cudaSuccess) return (int)e__;         \
   } while (0)
 
+// Programmatic dependent launch (the kernels of one update form a chain of dependent launches: schedule -> critic gradient ->
+// Adam -> schedule -> actor gradient -> Adam).  A kernel launched with launch_pdl may be scheduled while its predecessor in
+// the stream is still running; it must call pdl_wait() before it touches global memory (blocks until the predecessor grid
+// has completed and its writes are visible).  pdl_wait() also releases the NEXT kernel of the chain for scheduling, so the
+// launch latency between two dependent kernels (~2 us each, a tenth of the small-batch update) overlaps the running kernel.
+// EVERY kernel of such a chain has to call pdl_wait(): completion of a grid implies completion of its predecessors only if
+// the grid itself waited.  Inside stream capture the attribute becomes a programmatic edge of the CUDA graph.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, P(args)...);
+}
+
 // Padded row stride (odd number of elements) so that "thread r touches row r" is bank-conflict free.
 __host__ __device__ constexpr int pad_odd(int w) { return (w & 1) ? w : w + 1; }
 

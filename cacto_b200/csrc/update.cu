@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
                                                        const float* __restrict__ done, const float* __restrict__ weights, float inv_B,
                                                        float* __restrict__ grad, float* __restrict__ rtg_out, float* __restrict__ V_out,
                                                        float* __restrict__ Vt_out, float* __restrict__ loss_out, int64_t B) {
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   CriticSmem<S>& sm = *reinterpret_cast<CriticSmem<S>*>(smem_raw);
   const CriticLayout L(P.ns);
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
                                                       const float* __restrict__ cwT, const float* __restrict__ state,
                                                       const double* __restrict__ term, float inv_B, float* __restrict__ grad,
                                                       float* __restrict__ actions_out, int64_t B) {
+  pdl_wait();
   constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA, NS = NX + 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ActorSmem<S>& sm = *reinterpret_cast<ActorSmem<S>*>(smem_raw);
@@ -741,6 +743,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __re
                                               float alpha, const float* __restrict__ alpha_dev, float omb1, float omb2, float eps,
                                               float* __restrict__ target, float tau,
                                               float* __restrict__ pT, LayerTable T, int64_t n) {
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i];
@@ -768,6 +771,7 @@ __global__ void __launch_bounds__(256) k_adam_peer(float* __restrict__ p, PeerTa
                                                    float* __restrict__ m, float* __restrict__ v, const float* __restrict__ alpha_dev, float omb1,
                                                    float omb2, float eps, float* __restrict__ target, float tau, float* __restrict__ pT,
                                                    LayerTable T, int64_t n) {
+  pdl_wait();
   // words [0, CACTO_MAX_PEERS) of a rank's flag row: arrival epochs written by the peers; [CACTO_MAX_PEERS]: number of steps this
   // rank has completed (the epoch base, never rewound -- unlike the Adam step counter, which graph capture restores);
   // [CACTO_MAX_PEERS + 1]: CTA ticket of the running launch
@@ -863,19 +867,19 @@ static int launch_actor_grad(const cacto_sys_params& P, const float* aw, const f
   if (pick_tile(B) == 16) {
     auto k = k_actor_grad<SYS, 16>;
     if (int e = smem_attr(k, sizeof(ActorSmem<16>))) return e;
-    k<<<(unsigned)((B + 15) / 16), UP_NT, sizeof(ActorSmem<16>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
+    if (cudaError_t le = launch_pdl(k, (unsigned)((B + 15) / 16), UP_NT, sizeof(ActorSmem<16>), st, P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B)) return (int)le;
   } else if (pick_tile(B) == 8) {
     auto k = k_actor_grad<SYS, 8>;
     if (int e = smem_attr(k, sizeof(ActorSmem<8>))) return e;
-    k<<<(unsigned)((B + 7) / 8), UP_NT, sizeof(ActorSmem<8>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
+    if (cudaError_t le = launch_pdl(k, (unsigned)((B + 7) / 8), UP_NT, sizeof(ActorSmem<8>), st, P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B)) return (int)le;
   } else if (pick_tile(B) == 4) {
     auto k = k_actor_grad<SYS, 4>;
     if (int e = smem_attr(k, sizeof(ActorSmem<4>))) return e;
-    k<<<(unsigned)((B + 3) / 4), UP_NT, sizeof(ActorSmem<4>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
+    if (cudaError_t le = launch_pdl(k, (unsigned)((B + 3) / 4), UP_NT, sizeof(ActorSmem<4>), st, P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B)) return (int)le;
   } else {
     auto k = k_actor_grad<SYS, 2>;
     if (int e = smem_attr(k, sizeof(ActorSmem<2>))) return e;
-    k<<<(unsigned)((B + 1) / 2), UP_NT, sizeof(ActorSmem<2>), st>>>(P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B);
+    if (cudaError_t le = launch_pdl(k, (unsigned)((B + 1) / 2), UP_NT, sizeof(ActorSmem<2>), st, P, aw, awT, cw, cwT, state, term, inv_B, grad, actions, B)) return (int)le;
   }
   CACTO_LAUNCH_CHECK();
   return 0;
@@ -903,27 +907,27 @@ extern "C" int cacto_critic_grad(const cacto_sys_params* p, const float* critic_
   if (pick_tile(B) == 16) {
     auto k = k_critic_grad<16>;
     if (int e = smem_attr(k, sizeof(CriticSmem<16>))) return e;
-    k<<<(unsigned)((B + 15) / 16), UP_NT, sizeof(CriticSmem<16>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
+    if (cudaError_t le = launch_pdl(k, (unsigned)((B + 15) / 16), UP_NT, sizeof(CriticSmem<16>), st, *p, critic_params, critic_params_T, target_params, w_S, mc, state,
                                                                         state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
-                                                                        V_target_s, loss, B);
+                                                                        V_target_s, loss, B)) return (int)le;
   } else if (pick_tile(B) == 8) {
     auto k = k_critic_grad<8>;
     if (int e = smem_attr(k, sizeof(CriticSmem<8>))) return e;
-    k<<<(unsigned)((B + 7) / 8), UP_NT, sizeof(CriticSmem<8>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
+    if (cudaError_t le = launch_pdl(k, (unsigned)((B + 7) / 8), UP_NT, sizeof(CriticSmem<8>), st, *p, critic_params, critic_params_T, target_params, w_S, mc, state,
                                                                      state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
-                                                                     V_target_s, loss, B);
+                                                                     V_target_s, loss, B)) return (int)le;
   } else if (pick_tile(B) == 4) {
     auto k = k_critic_grad<4>;
     if (int e = smem_attr(k, sizeof(CriticSmem<4>))) return e;
-    k<<<(unsigned)((B + 3) / 4), UP_NT, sizeof(CriticSmem<4>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
+    if (cudaError_t le = launch_pdl(k, (unsigned)((B + 3) / 4), UP_NT, sizeof(CriticSmem<4>), st, *p, critic_params, critic_params_T, target_params, w_S, mc, state,
                                                                      state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
-                                                                     V_target_s, loss, B);
+                                                                     V_target_s, loss, B)) return (int)le;
   } else {
     auto k = k_critic_grad<2>;
     if (int e = smem_attr(k, sizeof(CriticSmem<2>))) return e;
-    k<<<(unsigned)((B + 1) / 2), UP_NT, sizeof(CriticSmem<2>), st>>>(*p, critic_params, critic_params_T, target_params, w_S, mc, state,
+    if (cudaError_t le = launch_pdl(k, (unsigned)((B + 1) / 2), UP_NT, sizeof(CriticSmem<2>), st, *p, critic_params, critic_params_T, target_params, w_S, mc, state,
                                                                      state_next, partial_rtg, dVdx, done, weights, inv_B, grad, rtg, V,
-                                                                     V_target_s, loss, B);
+                                                                     V_target_s, loss, B)) return (int)le;
   }
   CACTO_LAUNCH_CHECK();
   return 0;
@@ -982,6 +986,7 @@ extern "C" int cacto_critic_forward(const cacto_sys_params* p, const float* crit
 // CUDA graph of the update can be replayed without host-side scalars.  Also clears `zero_me` (loss accumulator).
 __global__ void k_adam_schedule(long long* __restrict__ step, const float* __restrict__ boundaries, const float* __restrict__ values,
                                 int nb, float beta1, float beta2, float* __restrict__ alpha_out, float* __restrict__ zero_me) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const long long it = step[0];
   int k = 0;
@@ -996,8 +1001,9 @@ __global__ void k_adam_schedule(long long* __restrict__ step, const float* __res
 extern "C" int cacto_adam_schedule(int64_t* step, const float* boundaries, const float* values, int32_t nb, float beta1, float beta2,
                                    float* alpha_out, float* zero_or_null, void* stream) {
   if (!step || !values || !alpha_out || (nb > 0 && !boundaries) || nb < 0) return CACTO_E_ARG;
-  k_adam_schedule<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(step), boundaries, values, nb, beta1, beta2, alpha_out,
-                                                      zero_or_null);
+  if (cudaError_t le = launch_pdl(k_adam_schedule, 1, 32, 0, (cudaStream_t)stream, reinterpret_cast<long long*>(step), boundaries, values, nb,
+                                  beta1, beta2, alpha_out, zero_or_null))
+    return (int)le;
   CACTO_LAUNCH_CHECK();
   return 0;
 }
@@ -1015,8 +1021,9 @@ extern "C" int cacto_adam_step(float* params, float* grad, float* m, float* v, f
   } else if (n != total) {
     return CACTO_E_SIZE;
   }
-  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grad, m, v, alpha_t, alpha_dev_or_null, 1.f - beta1, 1.f - beta2, eps,
-                                                                       target_or_null, tau, params_T_or_null, T, n);
+  if (cudaError_t le = launch_pdl(k_adam, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, params, grad, m, v, alpha_t, alpha_dev_or_null,
+                                  1.f - beta1, 1.f - beta2, eps, target_or_null, tau, params_T_or_null, T, n))
+    return (int)le;
   CACTO_LAUNCH_CHECK();
   return 0;
 }
@@ -1047,8 +1054,9 @@ extern "C" int cacto_adam_step_peer(float* params, const float* const* peer_grad
   }
   int64_t ctas = (n + 255) / 256;
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
-  k_adam_peer<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(params, R, zero_other_or_null, n_other, m, v, alpha_dev, 1.f - beta1,
-                                                                            1.f - beta2, eps, target_or_null, tau, params_T_or_null, T, n);
+  if (cudaError_t le = launch_pdl(k_adam_peer, (unsigned)ctas, 256, 0, (cudaStream_t)stream, params, R, zero_other_or_null, n_other, m, v, alpha_dev,
+                                  1.f - beta1, 1.f - beta2, eps, target_or_null, tau, params_T_or_null, T, n))
+    return (int)le;
   CACTO_LAUNCH_CHECK();
   return 0;
 }
