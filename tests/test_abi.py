@@ -77,6 +77,25 @@ def test_bad_arguments_are_rejected_without_launching():
     assert lib.cacto_segtree_update(null, null, 64, null, null, 4, null, null) == -1
     assert lib.cacto_segtree_reduce(C.c_void_p(8), null, 63, 0, 10, C.c_void_p(8), null) == -4   # capacity not a power of two
     assert lib.cacto_rtg_window(null, 1, null, null, 3, 5, 0, null, null, null, null, null, null, null) == -1
+    # data-parallel entry points: peer tables and regions
+    one = C.c_void_p(16)
+    tbl = (C.c_void_p * 2)(16, 16)
+    assert lib.cacto_adam_step_peer(null, tbl, tbl, 2, 0, null, 0, one, one, one, 0.9, 0.999, 1e-7, null, 0.0, null, 0, 7, 3, 8, 0, null) == -1
+    assert lib.cacto_adam_step_peer(one, tbl, tbl, 9, 0, null, 0, one, one, one, 0.9, 0.999, 1e-7, null, 0.0, null, 0, 7, 3, 8, 0, null) == -1   # > CACTO_MAX_PEERS
+    assert lib.cacto_adam_step_peer(one, tbl, tbl, 2, 2, null, 0, one, one, one, 0.9, 0.999, 1e-7, null, 0.0, null, 0, 7, 3, 8, 0, null) == -1   # rank >= world
+    assert lib.cacto_adam_step_peer(one, tbl, tbl, 2, 0, null, 0, one, one, one, 0.9, 0.999, 1e-7, null, 0.0, one, 1, 7, 3, 8, 0, null) == -4    # n != critic size
+    out = C.c_void_p()
+    assert lib.cacto_peer_alloc(0, C.byref(out)) == -1 and lib.cacto_peer_free(null) == -1
+    assert lib.cacto_peer_export(null, null) == -1 and lib.cacto_peer_open(null, C.byref(out)) == -1 and lib.cacto_peer_close(null) == -1
+
+
+def test_peer_region_layout():
+    """Host-side layout of the peer-memory block: two 128-byte flag rows, then 128-byte-aligned gradient blocks."""
+    from cacto_b200.parallel import PeerReduce
+    for nc, na in ((29377, 67330), (30017, 70918), (1, 1)):
+        total = PeerReduce.region_bytes(nc, na)
+        assert total % 128 == 0 and total >= 256 + 4 * (nc + na)
+        assert total - (256 + 4 * (nc + na)) < 256
 
 
 def test_product_path_fails_loudly_without_cuda():
