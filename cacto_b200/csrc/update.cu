@@ -105,14 +105,45 @@ struct CriticPtrs {
   const float* b[5];
   const float* W4;
 };
-__device__ __forceinline__ void load_critic_small(CriticSmall& d, const float* __restrict__ w, const CriticLayout& L) {
-  for (int i = threadIdx.x; i < L.ns * CR_H1; i += UP_NT) d.W1[i] = w[L.W[0] + i];
-  for (int i = threadIdx.x; i < CW; i += UP_NT) {
-    const int l = i < CR_H1 ? 0 : (i < CR_H1 + CR_H2 ? 1 : (i < CR_H1 + CR_H2 + CR_H3 ? 2 : 3));
-    d.b[i] = w[L.b[l] + (i - koff(l))];
+// The small-parameter blocks are contiguous pieces of the flat parameter vector (16-byte aligned, sizes multiples of 16 bytes):
+// thread 0 queues them as TMA bulk copies on one mbarrier -- one L2 round trip for the whole prologue instead of a chain of
+// dependent LDG -> STS loops (ncu at B = 64: 19 % of the actor kernel's stall samples sat in its first 400 instructions).
+__device__ __forceinline__ void bulk_g2s(void* sdst, const float* __restrict__ gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void small_bar_init(uint64_t* bar) {          // thread 0, before WeightPipe::init (which fences and syncs)
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+}
+__device__ __forceinline__ void small_bar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void small_bar_wait(uint64_t* bar) {           // all threads; the barrier completes exactly once per kernel
+  const uint32_t mb = smem_u32(bar);
+  uint32_t done = 0;
+  unsigned spins = 0;
+  while (!done) {
+    if (++spins > (1u << 24)) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mb), "r"(0u)
+        : "memory");
   }
-  for (int i = threadIdx.x; i < CR_H4; i += UP_NT) d.w5[i] = w[L.W[4] + i];
-  if (threadIdx.x == 0) d.b[CW] = w[L.b[4]];
+}
+__host__ __device__ __forceinline__ uint32_t critic_small_bytes(const CriticLayout& L) { return 4u * (uint32_t)(L.ns * CR_H1 + CW + CR_H4); }
+// thread 0 only (after small_bar_expect)
+__device__ __forceinline__ void load_critic_small(CriticSmall& d, const float* __restrict__ w, const CriticLayout& L, uint64_t* bar) {
+  bulk_g2s(d.W1, w + L.W[0], 4u * (uint32_t)(L.ns * CR_H1), bar);
+  bulk_g2s(d.b + koff(0), w + L.b[0], 4u * CR_H1, bar);
+  bulk_g2s(d.b + koff(1), w + L.b[1], 4u * CR_H2, bar);
+  bulk_g2s(d.b + koff(2), w + L.b[2], 4u * CR_H3, bar);
+  bulk_g2s(d.b + koff(3), w + L.b[3], 4u * CR_H4, bar);
+  bulk_g2s(d.w5, w + L.W[4], 4u * CR_H4, bar);
+  d.b[CW] = w[L.b[4]];
 }
 __device__ __forceinline__ CriticPtrs critic_ptrs(const CriticSmall& d) {
   CriticPtrs p;
@@ -129,11 +160,16 @@ struct ActorSmall {
   alignas(16) float W3[ACTOR_H * CACTO_MAX_NA];
   float b3[8];
 };
-__device__ __forceinline__ void load_actor_small(ActorSmall& d, const float* __restrict__ w, const ActorLayout& L) {
-  for (int i = threadIdx.x; i < L.ns * ACTOR_H; i += UP_NT) d.W1[i] = w[L.W1 + i];
-  for (int i = threadIdx.x; i < ACTOR_H; i += UP_NT) { d.b1[i] = w[L.b1 + i]; d.b2[i] = w[L.b2 + i]; }
-  for (int i = threadIdx.x; i < ACTOR_H * L.na; i += UP_NT) d.W3[i] = w[L.W3 + i];
-  if (threadIdx.x < L.na) d.b3[threadIdx.x] = w[L.b3 + threadIdx.x];
+__host__ __device__ __forceinline__ uint32_t actor_small_bytes(const ActorLayout& L) {
+  return 4u * (uint32_t)(L.ns * ACTOR_H + 2 * ACTOR_H + ACTOR_H * L.na);
+}
+// thread 0 only (after small_bar_expect)
+__device__ __forceinline__ void load_actor_small(ActorSmall& d, const float* __restrict__ w, const ActorLayout& L, uint64_t* bar) {
+  bulk_g2s(d.W1, w + L.W1, 4u * (uint32_t)(L.ns * ACTOR_H), bar);
+  bulk_g2s(d.b1, w + L.b1, 4u * ACTOR_H, bar);
+  bulk_g2s(d.b2, w + L.b2, 4u * ACTOR_H, bar);
+  bulk_g2s(d.W3, w + L.W3, 4u * (uint32_t)(ACTOR_H * L.na), bar);
+  for (int j = 0; j < L.na; ++j) d.b3[j] = w[L.b3 + j];
 }
 
 // Forward pass of the sine critic for a tile, activations ping-ponging between two [S][ld] scratch
@@ -169,7 +205,7 @@ __device__ __forceinline__ void critic_forward_tile(WeightPipe& pipe, SM& sm, in
 template <int S>
 struct CriticSmem {
   alignas(128) float WB[2 * W_CHUNK];
-  uint64_t bar[2];
+  uint64_t bar[2], bar_small;
   WeightSeq seq;
   CriticSmall sc, st;                       // critic / target critic small parameters
   alignas(16) float X2[2 * S][NSP];         // rows [0, S): normalised state, rows [S, 2S): normalised next state
@@ -208,15 +244,20 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
     }
     seq_push_critic_bwd(sm.seq, L, cwT);
     sm.loss = 0.f;
+    small_bar_init(&sm.bar_small);
   }
   pipe.init(sm.WB, sm.bar);
   pipe.issue(sm.seq.ptr[0], sm.seq.first[0]);
+  if (tid == 0) {
+    small_bar_expect(&sm.bar_small, 2u * critic_small_bytes(L));
+    load_critic_small(sm.sc, cw, L, &sm.bar_small);
+    load_critic_small(sm.st, tw, L, &sm.bar_small);
+  }
   float (*XN)[NSP] = sm.X2;
   load_normalised<S>(P, state, row0, rows, XN);
   if (!mc) load_normalised<S>(P, state_next, row0, rows, sm.X2 + S);
-  load_critic_small(sm.sc, cw, L);
-  load_critic_small(sm.st, tw, L);
   const CriticPtrs cp = critic_ptrs(sm.sc), tp = critic_ptrs(sm.st);
+  small_bar_wait(&sm.bar_small);
   __syncthreads();
 
   // ---- target critic: V_t(s_next) for the TD(n) tail (NeuralNetwork.py:157-158) and V_t(s) (:178)
@@ -399,7 +440,7 @@ __global__ void __launch_bounds__(UP_NT) k_critic_grad(const __grid_constant__ c
 template <int S>
 struct ActorSmem {
   alignas(128) float WB[2 * W_CHUNK];
-  uint64_t bar[2];
+  uint64_t bar[2], bar_small;
   WeightSeq seq;
   ActorSmall sa;
   CriticSmall sc;
@@ -437,13 +478,18 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
     seq_push_critic_fwd(sm.seq, LC, cw);
     seq_push_critic_bwd(sm.seq, LC, cwT);
     seq_push<ACTOR_H>(sm.seq, awT + LA.W2, ACTOR_H);
+    small_bar_init(&sm.bar_small);
   }
   pipe.init(sm.WB, sm.bar);
   pipe.issue(sm.seq.ptr[0], sm.seq.first[0]);
+  if (tid == 0) {
+    small_bar_expect(&sm.bar_small, actor_small_bytes(LA) + critic_small_bytes(LC));
+    load_actor_small(sm.sa, aw, LA, &sm.bar_small);
+    load_critic_small(sm.sc, cw, LC, &sm.bar_small);
+  }
   load_normalised<S>(P, state, row0, rows, sm.XN);
-  load_actor_small(sm.sa, aw, LA);
-  load_critic_small(sm.sc, cw, LC);
   const CriticPtrs cp = critic_ptrs(sm.sc);
+  small_bar_wait(&sm.bar_small);
   __syncthreads();
   // ---- actor forward (NeuralNetwork.py:185)
   tile_gemm<S, ACTOR_H, UP_NT, false>(&sm.XN[0][0], NSP, NS, sm.sa.W1, ACTOR_H, [&](int r, int c, const float4& a) {
