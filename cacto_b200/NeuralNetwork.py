@@ -16,6 +16,7 @@ variants (NeuralNetwork.py:65-93,110-128) run on the generic one-CTA-per-sample 
 (``Network.kind == 'critic_generic'``), with the same methods and return values.
 """
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -32,7 +33,7 @@ class Network:
     accumulator).  kind: 'actor' (LeakyReLU 0.3), 'critic_sine', or 'critic_generic' (any layer table, ``acts`` per layer:
     'sin' | 'elu' | 'leaky' | 'linear'; no transposed copy)."""
 
-    _registry = {}
+    _registry = weakref.WeakValueDictionary()      # params address -> Network (apply_gradients looks the owner up); weak: GPU blocks are freed with the net
 
     def __init__(self, kind, ns, na, dims, acts=None):
         self.kind, self.ns, self.na, self.dims = kind, int(ns), int(na), list(dims)
@@ -97,7 +98,10 @@ class Network:
 
     def load_weights(self, path):
         """``.npz`` written by save_weights, or a Keras ``.h5`` file written by the reference (RL.py:91-97,191-195)."""
+        import os
         path = str(path)
+        if path.endswith('.h5') and not os.path.exists(path) and os.path.exists(path[:-3] + '.npz'):
+            path = path[:-3] + '.npz'
         if path.endswith('.h5'):
             from .h5weights import load_keras_weights
             self.set_weights(load_keras_weights(path, self.ns))

@@ -79,9 +79,11 @@ class RL_AC:
 
         if recover_training is not None:
             path, n_try, step = str(recover_training[0]), recover_training[1], recover_training[2]
-            self.actor_model.load_weights("{}/N_try_{}/actor_{}".format(path, n_try, step))
-            self.critic_model.load_weights("{}/N_try_{}/critic_{}".format(path, n_try, step))
-            self.target_critic.load_weights("{}/N_try_{}/target_critic_{}".format(path, n_try, step))
+            # the reference's archive layout (RL.py:95-97): <path>/N_try_<n>/<net>_<step>.h5; Network.load_weights falls back to
+            # the .npz of the same stem when no .h5 is there
+            self.actor_model.load_weights("{}/N_try_{}/actor_{}.h5".format(path, n_try, step))
+            self.critic_model.load_weights("{}/N_try_{}/critic_{}.h5".format(path, n_try, step))
+            self.target_critic.load_weights("{}/N_try_{}/target_critic_{}.h5".format(path, n_try, step))
         else:
             self.target_critic.set_weights(self.critic_model.get_weights())
         if self.dist is not None:                       # identical replicas: broadcast rank 0's initial weights
@@ -109,11 +111,23 @@ class RL_AC:
             allreduce_sum(net.grad, self.dist)
             opt.step(net, target=target, tau=tau, prepared=prepared)
 
+    def peer_barrier(self):
+        """Host-level rendezvous of the data-parallel ranks before a run of peer-memory updates.  k_adam_peer spins on the
+        arrival flags of its peers and traps after 20 s; in the CACTO loop the ranks reach the update phase after host-side TO
+        solves whose duration differs per rank by far more than that, so the skew is absorbed HERE (an NCCL barrier blocks the
+        host, not a kernel): afterwards all ranks launch their updates in lock-step.  No-op without the peer exchange."""
+        if self._peer is not None:
+            torch.cuda.current_stream().synchronize()
+            self.dist.barrier()
+
     def update(self, state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
-               batch_size=None, fuse_target=False):
+               batch_size=None, fuse_target=False, synced=False):
         """RL.py:101-111.  ``fuse_target`` additionally performs update_target inside the critic's Adam launch
         (used by learn_and_update; the target is only read again at the next critic gradient, so the result is
-        identical to calling update_target afterwards)."""
+        identical to calling update_target afterwards).  ``synced``: the caller has already called ``peer_barrier`` for this
+        run of updates (learn_and_update does, once per call)."""
+        if not synced:
+            self.peer_barrier()
         world = self.dist.get_world_size() if self.dist is not None else 1
         gb = state_batch.shape[0] * world
         critic_grad, reward_to_go_batch, critic_value, target_critic_value = self.NN.compute_critic_grad(
@@ -170,6 +184,7 @@ class RL_AC:
     def learn_and_update(self, update_step_counter, buffer, ep):
         """RL.py:120-143."""
         graph = getattr(self, 'update_graph', None)
+        self.peer_barrier()                             # data-parallel ranks arrive here with minutes of skew (host TO solves)
         for _ in range(int(self.conf.UPDATE_LOOPS[ep])):
             if graph is not None:                       # captured update: the sampled rows land in the graph's input tensors
                 batch_idxes = buffer.sample(out=graph.io)[7]
@@ -178,7 +193,7 @@ class RL_AC:
                 state_batch, partial_reward_to_go_batch, state_next_rollout_batch, dVdx_batch, d_batch, term_batch, weights_batch, batch_idxes = buffer.sample()
                 reward_to_go_batch, critic_value, target_critic_value = self.update(
                     state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
-                    fuse_target=True)
+                    fuse_target=True, synced=True)
             if self.conf.prioritized_replay_alpha != 0:
                 buffer.update_priorities(batch_idxes, reward_to_go_batch, critic_value, target_critic_value)
             update_step_counter += 1
@@ -196,8 +211,8 @@ class RL_AC:
         self.target_critic.save_weights(d + "/target_critic_{}".format(update_step_counter))
 
     # ------------------------------------------------------------------------------ reward-to-go
-    def rtg_batch(self, TO_states_list, TO_step_cost_list):
-        return _rtg_batch(self.conf, TO_states_list, TO_step_cost_list)
+    def rtg_batch(self, TO_states_list, TO_step_cost_list, lengths=None):
+        return _rtg_batch(self.conf, TO_states_list, TO_step_cost_list, lengths)
 
     def RL_Solve(self, TO_controls, TO_states, TO_step_cost):
         """RL.py:145-189: returns the reference's 9-tuple (NumPy).  env_RL = 0 (every conf) takes states and rewards from the
@@ -286,10 +301,37 @@ class RL_AC:
         flags = torch.empty(B, dtype=torch.int32, device=dev)
         rewards = torch.full((T_max + 1, B), float('nan'), dtype=torch.float64, device=dev) if with_reward else None
         self._launch_rollout(ep, ics, hz, T_max, states, controls, flags, rewards, B, engine)
+        self._retry_flagged(ep, ics, hz, T_max, states, controls, flags, rewards, engine)
         out = dict(states=states, controls=controls, horizon=hz, success=flags)
         if with_reward:
             out['rewards'] = rewards
         return out
+
+    def _retry_flagged(self, ep, ics, hz, T_max, states, controls, flags, rewards, engine=None):
+        """The fp16-split engines ('tc', 'tc2') flag a rollout failed when a hidden activation leaves the fp16 range (+-2047
+        after scaling, rollout_tc16.cu) -- a limit the reference does not have: RL.py:229-231 aborts on NaN only and trained
+        actors are unbounded.  Flagged rollouts are therefore rolled out again on the fp32 'fma' engine and
+        patched into the outputs; only rollouts that fail there too (a NaN state, as in the reference) stay flagged.
+        Costs one device->host read of the failure count per call.  Returns the number of rollouts re-run."""
+        if ep == 0 or (engine or self.rollout_engine) not in ('tc', 'tc2') or self.actor_model.ns > 8:
+            return 0
+        bad = (flags == 0).nonzero().reshape(-1)
+        n = int(bad.numel())
+        if n == 0:
+            return 0
+        dev = flags.device
+        ns, na = states.shape[1], controls.shape[1]
+        st = torch.full((T_max + 1, ns, n), float('nan'), dtype=torch.float64, device=dev)
+        ct = torch.full((T_max, na, n), float('nan'), dtype=torch.float64, device=dev)
+        fl = torch.empty(n, dtype=torch.int32, device=dev)
+        rw = torch.full((T_max + 1, n), float('nan'), dtype=torch.float64, device=dev) if rewards is not None else None
+        self._launch_rollout(ep, ics[bad].contiguous(), hz[bad].contiguous(), T_max, st, ct, fl, rw, n, 'fma')
+        states[:, :, bad] = st
+        controls[:, :, bad] = ct
+        flags[bad] = fl
+        if rewards is not None:
+            rewards[:, bad] = rw
+        return n
 
     def rollout_to_host(self, ics_host, ep, states_host, controls_host, flags_host, mode='pipelined', engine=None, n_chunks=8):
         """Host-to-host rollouts for the TO feeder: ``ics_host`` [B, ns] fp64 (pinned) -> ``states_host``
@@ -353,6 +395,14 @@ class RL_AC:
             controls_host.copy_(buf[1], non_blocking=True)
             flags_host.copy_(buf[2], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        # fp16-range failures of the 'tc' engines (see _retry_flagged): re-run on 'fma' and patch the host buffers
+        if ep != 0 and (engine or self.rollout_engine) in ('tc', 'tc2') and self.actor_model.ns <= 8:
+            bad = (flags_host == 0).nonzero().reshape(-1)
+            if bad.numel() > 0:
+                r = self.rollout_batch(ics_host[bad], ep, horizon=hz_np[bad.numpy()], engine='fma')
+                states_host[:, :, bad] = r['states'].cpu()
+                controls_host[:, :, bad] = r['controls'].cpu()
+                flags_host[bad] = r['success'].cpu()
         return hz_np
 
     def create_TO_init(self, ep, ICS):
@@ -396,8 +446,12 @@ class UpdateGraph:
         for o, n in ((rl.critic_optimizer, rl.critic_model), (rl.actor_optimizer, rl.actor_model)):
             o.moments(n)
             o._device_state(dev)
+        # In peer mode the gradient blocks are mapped by the other ranks, whose k_adam_peer of the previous eager update may still be
+        # summing them: nothing may clear them before every rank's stream has drained (update.cu: "a rank never clears its own block").
+        self._quiesce()
         for n in nets:
             n.grad.zero_()
+        self._quiesce()
         # snapshot the training state, warm up on a side stream (lazy initialisation), capture, restore
         snap = [(t, t.clone()) for n in nets for t in (n.params, n.params_T) if t is not None]
         snap += [(t, t.clone()) for o in opts for st in o._state.values() for t in st]
@@ -417,9 +471,17 @@ class UpdateGraph:
             t.copy_(old)
         for o, it in zip(opts, its):
             o.iterations = it
+        self._quiesce()
         for n in nets:
             n.grad.zero_()
+        self._quiesce()
+
+    def _quiesce(self):
+        """All launches of this rank done and -- data-parallel -- of every other rank too."""
         torch.cuda.synchronize()
+        if self.rl._peer is not None:
+            self.rl.dist.barrier()
+            torch.cuda.synchronize()
 
     def replay(self):
         self.graph.replay()

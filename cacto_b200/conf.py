@@ -83,6 +83,13 @@ def get_conf(system_id, **overrides):
     s = dict(_SYSTEMS[system_id])
     c = dict(_COMMON)
     c['system_id'] = system_id
+    # overrides of PRIMARY constants (REPLAY_SIZE, BATCH_SIZE, NSTEPS, dt, learning rates, ...) come first so that everything the
+    # reference's conf modules derive from them (nsteps_TD_N, LR-schedule boundaries, x_init_max, state_norm_arr, ...) follows
+    for k, v in overrides.items():
+        if k in s:
+            s[k] = v
+        elif k in c:
+            c[k] = v
     for k in ('prioritized_replay_eps', 'fresh_factor'):
         if k in s:
             c[k] = s.pop(k)

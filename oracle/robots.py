@@ -159,6 +159,12 @@ class Chain:
         (tau_c = 0, no contacts)."""
         return np.linalg.solve(self.crba(q), np.asarray(tau) - self.nle(q, v))
 
+    def minv(self, q):
+        """Minv as aba_derivatives returns it (symmetrised inverse of the CRBA matrix) without the derivative passes:
+        what Env.derivative needs (environment.py:100-104 reads only data.Minv)."""
+        Minv = np.linalg.inv(self.crba(np.asarray(q, dtype=float)))
+        return 0.5 * (Minv + Minv.T)
+
     def aba_derivatives(self, q, v, tau, h=1e-30):
         """(ddq_dq, ddq_dv, Minv) as pin.computeABADerivatives leaves them in data
         (environment.py:120-126).  Exact via complex step."""
@@ -175,9 +181,7 @@ class Chain:
             vc = v.astype(complex)
             vc[j] += 1j * h
             ddq_dv[:, j] = np.imag(self.forward_dynamics(q, vc, tau)) / h
-        Minv = np.linalg.inv(self.crba(q))
-        Minv = 0.5 * (Minv + Minv.T)
-        return ddq_dq, ddq_dv, Minv
+        return ddq_dq, ddq_dv, self.minv(q)
 
 
 _Z3 = (0.0, 0.0, 0.0)

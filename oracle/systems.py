@@ -60,7 +60,7 @@ class Env:
 
     # environment.py:93-109
     def derivative(self, state, action):
-        _, _, Minv = self.chain.aba_derivatives(state[:self.nq], state[self.nq:self.nx], action)
+        Minv = self.chain.minv(state[:self.nq])           # = aba_derivatives(...)[2]; the derivative passes are not needed here
         Fu = np.zeros((self.nx + 1, self.nu))
         Fu[self.nv:-1, :] = Minv
         Fu[:self.nx, :] *= self.conf.dt
@@ -342,3 +342,54 @@ SYSTEMS = {'single_integrator': SingleIntegrator, 'double_integrator': DoubleInt
 
 def make_env(conf):
     return SYSTEMS[conf.system_id](conf)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The per-sample loops of simulate_batch / derivative_batch (environment.py:134-144) fanned over forked worker processes:
+# same arithmetic per sample, only the wall time changes (NumPy RNEA: ~10 ms per manipulator sample, ~40 ms per UR5 sample).
+# Used by the large-batch parity tests (B = 4096 / 16384) and by bench.py's CPU baseline, never by the product.
+_POOL_ENV = None
+
+
+def _pool_sim(args):
+    s, a = args
+    return np.array([_POOL_ENV.simulate(x, u) for x, u in zip(s, a)])
+
+
+def _pool_der(args):
+    s, a = args
+    return np.array([_POOL_ENV.derivative(x, u) for x, u in zip(s, a)])
+
+
+class PooledEnv:
+    """Wraps an oracle Env: simulate_batch / derivative_batch split the batch into chunks over ``procs`` forked workers;
+    every other attribute is the wrapped environment's."""
+
+    def __init__(self, env, procs=None):
+        import os
+        self._env = env
+        self._procs = int(procs or min(32, os.cpu_count() or 1))
+
+    def __getattr__(self, name):
+        return getattr(self._env, name)
+
+    def _map(self, fn, state, action):
+        import multiprocessing as mp
+        global _POOL_ENV
+        state, action = np.asarray(state), np.asarray(action)
+        B = len(state)
+        if self._procs <= 1 or B < 4 * self._procs:
+            _POOL_ENV = self._env
+            return fn((state, action))
+        _POOL_ENV = self._env                      # inherited by the forked workers
+        n = self._procs * 4
+        cuts = [B * i // n for i in range(n + 1)]
+        with mp.get_context('fork').Pool(self._procs) as pool:
+            parts = pool.map(fn, [(state[a:b], action[a:b]) for a, b in zip(cuts[:-1], cuts[1:]) if b > a])
+        return np.concatenate(parts, axis=0)
+
+    def simulate_batch(self, state, action):
+        return self._map(_pool_sim, state, action).astype(np.float32)
+
+    def derivative_batch(self, state, action):
+        return self._map(_pool_der, state, action).astype(np.float32)

@@ -42,3 +42,18 @@ def test_conf_matches_reference_dump(system):
             assert mine == v, f'{system}.{k}: {mine!r} != {v!r}'
         checked += 1
     assert checked > 60
+
+
+def test_overrides_of_primary_constants_reach_derived_values():
+    """conf_*.py derive the LR-schedule boundaries from REPLAY_SIZE / BATCH_SIZE, nsteps_TD_N, x_init_max[-1] and
+    state_norm_arr[-1] from NSTEPS and dt: an override of a primary constant must propagate (BASELINE configs 2 / 3 / 5 override
+    BATCH_SIZE)."""
+    from cacto_b200.conf import get_conf
+    a, b = get_conf('manipulator'), get_conf('manipulator', BATCH_SIZE=4096)
+    assert a.boundaries_schedule_LR_C[0] == 200 * 2 ** 16 / 64
+    assert b.boundaries_schedule_LR_C == [m * 2 ** 16 / 4096 for m in (200, 300, 400, 500)]
+    c = get_conf('car', NSTEPS=200, dt=0.1, REPLAY_SIZE=2 ** 12)
+    assert c.nsteps_TD_N == 50 and c.x_init_max[-1] == 199 * 0.1 and c.state_norm_arr[-1] == 20
+    assert c.boundaries_schedule_LR_A[0] == 200 * 2 ** 12 / 64
+    d = get_conf('ur5', nsteps_TD_N=7)                       # a derived value can still be overridden directly
+    assert d.nsteps_TD_N == 7

@@ -114,6 +114,87 @@ def test_one_update_step_matches_oracle(system, B):
             assert rel(m, r) < 1e-5
 
 
+# ---- BASELINE configs 2, 3, 5 at their full update batches (PER batch 4096, critic batch 16 384, UR5 shard) against the oracle.
+# The oracle's per-sample dynamics loops are fanned over worker processes (oracle.systems.PooledEnv: same arithmetic).
+LARGE = [('manipulator', 4096), ('car', 16384), ('ur5', 4096), ('double_integrator', 4096)]
+
+
+@pytest.mark.parametrize('system,B', LARGE)
+def test_large_batch_gradients_match_oracle(system, B):
+    conf, env, nn, rl, batch = make(system, B)
+    s, pr, sn, dv, d, term, w = batch
+    critic, target, actor = rl.critic_model.get_weights(), rl.target_critic.get_weights(), rl.actor_model.get_weights()
+    target = [t + 0.01 * np.random.default_rng(5).normal(size=t.shape).astype(np.float32) for t in target]
+    rl.target_critic.set_weights(target)
+    cg, rtg, V, Vt, loss = onn.critic_grad(critic, target, conf, 1e-2, s, sn, pr, dv, d, w)
+    g, g_rtg, g_V, g_Vt = nn.compute_critic_grad(rl.critic_model, rl.target_critic, s, sn, pr, dv, d, w)
+    assert rel(g_rtg, rtg) < 2e-5 and rel(g_V, V) < 2e-5 and rel(g_Vt, Vt) < 2e-5
+    assert abs(float(nn.last_critic_loss) - loss) <= 1e-4 * abs(loss)
+    for gv, rv in zip(g, cg):
+        assert rel(gv, rv) < 1e-4
+    oenv = osys.PooledEnv(osys.make_env(conf))
+    ag, actions, s_next, dQ = onn.actor_grad(actor, critic, conf, oenv, s, term)
+    ga, act = nn.compute_actor_grad(rl.actor_model, rl.critic_model, s, term, None, return_actions=True)
+    assert rel(act, actions) < 2e-5
+    for gv, rv in zip(ga, ag):
+        assert rel(gv, rv) < 1e-4
+
+
+@pytest.mark.parametrize('system,B', [('manipulator', 4096), ('car', 16384)])
+def test_large_batch_update_step_matches_oracle(system, B):
+    conf, env, nn, rl, batch = make(system, B)
+    s, pr, sn, dv, d, term, w = batch
+    critic, target, actor = rl.critic_model.get_weights(), rl.target_critic.get_weights(), rl.actor_model.get_weights()
+    oc, oa = onn.Adam(critic, conf.CRITIC_LEARNING_RATE), onn.Adam(actor, conf.ACTOR_LEARNING_RATE)
+    oenv = osys.PooledEnv(osys.make_env(conf))
+    out = onn.update(critic, target, actor, oc, oa, conf, 1e-2, oenv, (s, pr, sn, dv, d, term, w))
+    rtg, V, Vt = rl.update(s, sn, pr, dv, d, term, w, fuse_target=True)
+    assert rel(rtg, out['rtg']) < 2e-5 and rel(V, out['V']) < 2e-5
+    for m, r in zip(rl.critic_model.get_weights() + rl.actor_model.get_weights(), critic + actor):
+        assert rel(m, r) < 1e-4
+    for m, r in zip(rl.target_critic.get_weights(), target):
+        assert rel(m, r) < 1e-5
+
+
+# ---- conf.MC = 1 (NeuralNetwork.py:154-155: the target is the Monte-Carlo partial reward-to-go itself, no target critic, and
+# RL.py:134 skips update_target)
+@pytest.mark.parametrize('system,B', [('manipulator', 64), ('single_integrator', 128), ('car', 2400)])
+@pytest.mark.parametrize('w_S', [1e-2, 0.0])
+def test_mc_critic_gradient_matches_oracle(system, B, w_S):
+    conf, env, nn, rl, batch = make(system, B, w_S=w_S, MC=1)
+    assert conf.MC == 1
+    s, pr, sn, dv, d, term, w = batch
+    critic, target = rl.critic_model.get_weights(), rl.target_critic.get_weights()
+    cg, rtg, V, Vt, loss = onn.critic_grad(critic, target, conf, w_S, s, sn, pr, dv, d, w)
+    np.testing.assert_array_equal(rtg, pr)
+    g, g_rtg, g_V, g_Vt = nn.compute_critic_grad(rl.critic_model, rl.target_critic, s, sn, pr, dv, d, w)
+    assert (g_rtg.cpu().numpy() == pr).all()                # rtg IS the partial reward-to-go
+    assert rel(g_V, V) < 2e-5 and rel(g_Vt, Vt) < 2e-5
+    assert abs(float(nn.last_critic_loss) - loss) <= 1e-4 * abs(loss)
+    for gv, rv in zip(g, cg):
+        assert rel(gv, rv) < 1e-4
+
+
+def test_mc_update_leaves_target_untouched():
+    conf, env, nn, rl, batch = make('manipulator', 64, MC=1)
+    s, pr, sn, dv, d, term, w = batch
+    critic, target, actor = rl.critic_model.get_weights(), rl.target_critic.get_weights(), rl.actor_model.get_weights()
+    t0 = [t.copy() for t in target]
+    oc, oa = onn.Adam(critic, conf.CRITIC_LEARNING_RATE), onn.Adam(actor, conf.ACTOR_LEARNING_RATE)
+    onn.update(critic, target, actor, oc, oa, conf, 1e-2, osys.make_env(conf), (s, pr, sn, dv, d, term, w))
+    rl.update(s, sn, pr, dv, d, term, w, fuse_target=True)      # learn_and_update's call: the fused Polyak step must be skipped
+    for m, r in zip(rl.critic_model.get_weights() + rl.actor_model.get_weights(), critic + actor):
+        assert rel(m, r) < 1e-4
+    for m, r in zip(rl.target_critic.get_weights(), t0):
+        np.testing.assert_array_equal(m, r)
+    g = rl.make_update_graph(64)                                # and in the captured update
+    for k, v in zip(('state', 'state_next', 'partial_rtg', 'dVdx', 'done', 'term', 'weights'), (s, sn, pr, dv, d, term, w)):
+        g.io[k].copy_(torch.as_tensor(v))
+    g.replay()
+    for m, r in zip(rl.target_critic.get_weights(), t0):
+        np.testing.assert_array_equal(m, r)
+
+
 def test_fused_target_update_equals_separate():
     conf, env, nn, rl, batch = make('manipulator', 64)
     s, pr, sn, dv, d, term, w = batch

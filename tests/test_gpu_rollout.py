@@ -153,3 +153,40 @@ def test_rollout_to_host_modes_agree():
         assert np.abs(a[m] - b[m]).max() < 1e-5
         mc = np.broadcast_to(knots[:-1, None, :] & (np.arange(T)[:, None, None] < hz[None, None, :]), ct.shape)
         assert np.abs(ct.numpy()[mc] - ref['controls'].cpu().numpy()[mc]).max() < 1e-5
+
+
+def test_tc_engine_overflow_falls_back_to_fma():
+    """An actor whose hidden activations leave the fp16 range of the 'tc' engine (rollout_tc16.cu: +-2047 after scaling) must not
+    change the outcome: the reference aborts on NaN only (RL.py:229-231).  Flagged rollouts are re-run on 'fma'."""
+    conf, env, rl = setup('manipulator')
+    w = rl.actor_model.get_weights()
+    w[0] = w[0] * 1e3                       # first-layer pre-activations ~1e3 x larger: h1 overflows the fp16 high part
+    w[2] = w[2] * 1e-3                      # keep the actions (and the dynamics) in range
+    rl.actor_model.set_weights(w)
+    X0 = ics(conf, 300, 11)
+    X0[:, -1] = (conf.NSTEPS - 20) * conf.dt
+    ref = rl.rollout_batch(X0, 1, engine='fma')
+    assert ref['success'].cpu().numpy().all()
+    # the raw engine does flag them ...
+    dev = ref['states'].device
+    T = int(conf.NSTEPS)
+    st = torch.full_like(ref['states'], float('nan')); ct = torch.full_like(ref['controls'], float('nan'))
+    fl = torch.empty(300, dtype=torch.int32, device=dev)
+    rl._launch_rollout(1, torch.as_tensor(X0, device=dev), ref['horizon'], T, st, ct, fl, None, 300, 'tc')
+    assert (fl.cpu().numpy() == 0).any(), 'the scaled actor was meant to overflow the fp16 engine'
+    # ... and rollout_batch repairs them
+    out = rl.rollout_batch(X0, 1, engine='tc')
+    assert out['success'].cpu().numpy().all()
+    a, b = out['states'].cpu().numpy(), ref['states'].cpu().numpy()
+    m = ~np.isnan(b)
+    assert (np.isnan(a) == np.isnan(b)).all()
+    assert np.abs(a[m] - b[m]).max() <= 1e-4 * np.abs(b[m]).max()
+    # host-to-host path
+    sh = torch.empty((T + 1, conf.nb_state, 300), dtype=torch.float64).pin_memory()
+    ch = torch.empty((T, conf.nb_action, 300), dtype=torch.float64).pin_memory()
+    fh = torch.empty(300, dtype=torch.int32).pin_memory()
+    rl.rollout_to_host(torch.as_tensor(X0).pin_memory(), 1, sh, ch, fh)
+    assert fh.numpy().all()
+    hz = ref['horizon'].cpu().numpy()
+    for b_ in (0, 150, 299):
+        np.testing.assert_allclose(sh[:hz[b_] + 1, :, b_].numpy(), b[:hz[b_] + 1, :, b_], rtol=1e-4, atol=1e-6)
