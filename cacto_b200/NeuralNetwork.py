@@ -217,7 +217,32 @@ class NN:
         return V, dV
 
     # -- gradient launches (shared by the eager methods below and by RL_AC's CUDA-graph update) -----------
+    # Batch size from which the 'sine' critic / actor gradients run on the tensor-core kernels (csrc/update_tc.cu: 128-sample
+    # tiles, one tile per SM) instead of the fused fp32-FMA tile kernels (csrc/update.cu).  ``update_engine``: 'auto' | 'fma' | 'tc'.
+    TC_MIN_BATCH = 2048
+    update_engine = 'auto'
+
+    def _use_tc(self, B):
+        eng = self.update_engine
+        if eng not in ('auto', 'fma', 'tc'):
+            raise ValueError('unknown update engine %r' % (eng,))
+        return eng == 'tc' or (eng == 'auto' and B >= self.TC_MIN_BATCH)
+
+    def _tc_workspace(self, B):
+        need = int(lib.cacto_update_tc_workspace_bytes(B, self.conf.nb_state, self.conf.nb_action))
+        ws = getattr(self, '_tc_ws', None)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=_device())       # cudaMalloc: 256-byte aligned or better; checked by the callee
+            self._tc_ws = ws
+        return ws
+
     def launch_critic_grad(self, cm, tc, s, sn, pr, dv, d, w, inv_B, rtg, V, Vt, B):
+        if cm.kind == 'critic_sine' and self._use_tc(B):
+            ws = self._tc_workspace(B)
+            check(lib.cacto_critic_grad_tc(self._p, ptr(cm.params), ptr(tc.params), float(self.w_S), int(bool(self.conf.MC)), ptr(s), ptr(sn), ptr(pr),
+                                           ptr(dv), ptr(d), ptr(w), inv_B, ptr(cm.grad), ptr(rtg), ptr(V), ptr(Vt), ptr(self.last_critic_loss), B,
+                                           ptr(ws), ws.numel(), stream_ptr()), 'critic_grad_tc')
+            return
         if cm.kind == 'critic_generic':
             check(lib.cacto_critic_grad_generic(self._p, _lib.C.byref(cm.desc), ptr(cm.params), ptr(tc.params), float(self.w_S),
                                                 int(bool(self.conf.MC)), ptr(s), ptr(sn), ptr(pr), ptr(dv), ptr(d), ptr(w), inv_B, ptr(cm.grad),
@@ -228,6 +253,11 @@ class NN:
                                         ptr(self.last_critic_loss), B, stream_ptr()), 'critic_grad')
 
     def launch_actor_grad(self, am, cm, s, term, inv_B, actions, B):
+        if cm.kind == 'critic_sine' and self._use_tc(B):
+            ws = self._tc_workspace(B)
+            check(lib.cacto_actor_grad_tc(self._p, ptr(am.params), ptr(cm.params), ptr(s), ptr(term), inv_B, ptr(am.grad), ptr(actions), B,
+                                          ptr(ws), ws.numel(), stream_ptr()), 'actor_grad_tc')
+            return
         if cm.kind == 'critic_generic':
             # environment terms from the batched kernels of the reference-facing API (NeuralNetwork.py:185-204), network part generic
             act = self.eval(am, s)

@@ -116,9 +116,10 @@ class RL_AC:
         arrival flags of its peers and traps after 20 s; in the CACTO loop the ranks reach the update phase after host-side TO
         solves whose duration differs per rank by far more than that, so the skew is absorbed HERE (an NCCL barrier blocks the
         host, not a kernel): afterwards all ranks launch their updates in lock-step.  No-op without the peer exchange."""
-        if self._peer is not None:
+        barrier = getattr(self.dist, 'barrier', None)    # ranks simulated inside one process (tests) have nothing to wait for
+        if self._peer is not None and barrier is not None:
             torch.cuda.current_stream().synchronize()
-            self.dist.barrier()
+            barrier()
 
     def update(self, state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch, term_batch, weights_batch,
                batch_size=None, fuse_target=False, synced=False):
@@ -479,7 +480,7 @@ class UpdateGraph:
     def _quiesce(self):
         """All launches of this rank done and -- data-parallel -- of every other rank too."""
         torch.cuda.synchronize()
-        if self.rl._peer is not None:
+        if self.rl._peer is not None and getattr(self.rl.dist, 'barrier', None) is not None:
             self.rl.dist.barrier()
             torch.cuda.synchronize()
 

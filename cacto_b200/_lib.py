@@ -127,6 +127,10 @@ _SIGNATURES = {
     'cacto_critic_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 6 +
     [C.c_float] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]),
     'cacto_actor_grad': (C.c_int, [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_update_tc_workspace_bytes': (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    'cacto_critic_grad_tc': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 6 + [C.c_float] + [C.c_void_p] * 5 +
+                             [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_actor_grad_tc': (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_adam_schedule': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     'cacto_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p] + [C.c_float] * 3 + [C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int64, C.c_void_p]),

@@ -214,6 +214,23 @@ int cacto_actor_grad(const cacto_sys_params* p, const float* actor_params, const
                      const double* term, float inv_B, float* grad, float* actions /* [B][na] or NULL */,
                      int64_t B, void* stream);
 
+/* ---- N6 / N7 at large batch (B >= ~2 k: the PER batch 4096 and critic batch 16 384 of BASELINE configs 2, 3, 5) on tcgen05
+ *      tensor cores (csrc/update_tc.cu): same arguments, outputs and accumulate-into-grad contract as cacto_critic_grad /
+ *      cacto_actor_grad (NeuralNetwork.py:150-178 / :180-232), computed layer by layer over 128-sample tiles with fp16-split
+ *      operands (fp32-class products, fp32 accumulation in TMEM) and batch-reduction GEMMs for the weight gradients.  No
+ *      transposed parameter copies are needed.  workspace: caller-owned, 256-byte aligned, at least
+ *      cacto_update_tc_workspace_bytes(B, ns, na) bytes (~19 KB per sample; both calls of an update may share it: the actor
+ *      call reuses nothing of the critic call's contents). */
+int64_t cacto_update_tc_workspace_bytes(int64_t B, int32_t ns, int32_t na);
+int cacto_critic_grad_tc(const cacto_sys_params* p, const float* critic_params, const float* target_params, float w_S, int mc,
+                         const float* state, const float* state_next, const float* partial_rtg, const float* dVdx,
+                         const float* done, const float* weights, float inv_B, float* grad, float* rtg, float* V,
+                         float* V_target_s, float* loss /* [1], accumulated, or NULL */, int64_t B, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+int cacto_actor_grad_tc(const cacto_sys_params* p, const float* actor_params, const float* critic_params, const float* state,
+                        const double* term, float inv_B, float* grad, float* actions /* [B][na] or NULL */, int64_t B,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- N8/N9: tf.keras Adam step (RL.py:105,109; TF 2.11: m += (g-m)(1-b1), v += (g^2-v)(1-b2),
  *      p -= alpha_t m / (sqrt(v) + eps)) fused with the optional Polyak target update (RL.py:113-118:
  *      target = tau p + (1-tau) target), the refresh of the transposed copy and the zeroing of `grad`.
