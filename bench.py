@@ -35,6 +35,8 @@ FLOPS_PER_ENV_STEP = 2 * P_ACTOR_MACS + F_DYN
 # dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel per launch at the default workload, from the committed
 # `ncu --set full` captures under profiles/ (None until an engine has been captured)
 TRAFFIC_BYTES = {'tc': 8869376 + 998446080, 'tf32': 8953600 + 998347520}
+TRAFFIC_SOURCE = {'tc': 'profiles/r1_rollout_tc16_ncu_raw.csv (ncu --set full capture of this command; not re-measured in-run)',
+                  'tf32': 'profiles/r1_rollout_tc_ncu_raw.csv (ncu --set full capture; not re-measured in-run)'}
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
@@ -74,6 +76,114 @@ def cpu_rollout_rate(cores, rollouts_per_core):
         steps = sum(pool.map(_cpu_worker, [(i, rollouts_per_core, weights) for i in range(cores)]))
         dt = time.perf_counter() - t0
     return steps / dt, steps, dt
+
+
+def _update_batch(conf, B, seed):
+    """Synthetic replay rows of SURVEY.md 8(d): s, s_next ~ U(x_init), partial_rtg ~ U(-5, 0), dVdx ~ N(0, 1) (time column 0),
+    done ~ Bernoulli(0.5), term ~ Bernoulli(0.01), weights 1."""
+    rng = np.random.default_rng(seed)
+    ns = conf.nb_state
+    lo, hi = np.asarray(conf.x_init_min, float), np.asarray(conf.x_init_max, float)
+    s = rng.uniform(lo, hi, (B, ns)).astype(np.float32)
+    sn = rng.uniform(lo, hi, (B, ns)).astype(np.float32)
+    pr = rng.uniform(-5, 0, (B, 1)).astype(np.float32)
+    dv = rng.normal(size=(B, ns)).astype(np.float32)
+    dv[:, -1] = 0
+    d = (rng.uniform(size=(B, 1)) < 0.5).astype(np.float32)
+    term = (rng.uniform(size=(B, 1)) < 0.01).astype(np.float64)
+    w = np.ones((B, 1), np.float32)
+    return s, pr, sn, dv, d, term, w
+
+
+def cpu_update_baseline(system, B, cores, n=3, dyn_sample=None):
+    """C4 of BASELINE.md: the oracle's restatement of RL_AC.update (torch-CPU fp32 autograd with create_graph for the Sobolev
+    term, TF-style Adam, Polyak; per-sample Python loops for simulate_batch / derivative_batch as environment.py:134-144) on
+    `cores` torch threads.  With ``dyn_sample`` the per-sample dynamics loops run on that many rows and are scaled to B (stated)."""
+    import torch
+    from cacto_b200.conf import get_conf
+    from oracle import nn as onn, systems as osys
+    torch.set_num_threads(cores)
+    conf = get_conf(system)
+    env = osys.make_env(conf)
+    critic, actor = onn.init_critic_sine(conf.nb_state, seed=0), onn.init_actor(conf.nb_state, conf.nb_action, seed=1)
+    target = [c.copy() for c in critic]
+    oc, oa = onn.Adam(critic, conf.CRITIC_LEARNING_RATE), onn.Adam(actor, conf.ACTOR_LEARNING_RATE)
+    batch = _update_batch(conf, B, 0)
+    if dyn_sample is None or dyn_sample >= B:
+        onn.update(critic, target, actor, oc, oa, conf, 1e-2, env, batch)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            onn.update(critic, target, actor, oc, oa, conf, 1e-2, env, batch)
+        dt = (time.perf_counter() - t0) / n
+        return 1.0 / dt, f'{n} full updates of batch {B} ({dt:.3f} s each)'
+    # bounded: network part on the full batch with the per-sample dynamics replaced by a scaled sample
+    s, pr, sn, dv, d, term, w = batch
+    t0 = time.perf_counter()
+    env.simulate_batch(s[:dyn_sample], np.zeros((dyn_sample, conf.nb_action), np.float32))
+    env.derivative_batch(s[:dyn_sample], np.zeros((dyn_sample, conf.nb_action), np.float32))
+    t_dyn = (time.perf_counter() - t0) * B / dyn_sample
+
+    class _Env:                       # stand-in dynamics terms of the right shape: only the (scaled) cost of the real loops is charged
+        def simulate_batch(self, st, a):
+            return np.asarray(st, np.float32)
+
+        def derivative_batch(self, st, a):
+            return np.full((len(st), conf.nb_state, conf.nb_action), 1e-3, np.float32)
+    fake = _Env()
+    onn.update(critic, target, actor, oc, oa, conf, 1e-2, fake, batch)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        onn.update(critic, target, actor, oc, oa, conf, 1e-2, fake, batch)
+    t_net = (time.perf_counter() - t0) / n
+    dt = t_net + t_dyn
+    return 1.0 / dt, (f'batch {B}: torch-CPU network part measured on the full batch ({t_net:.3f} s, {cores} threads) + per-sample '
+                      f'simulate/derivative loops measured on {dyn_sample} rows and scaled to {B} ({t_dyn:.1f} s, 1 core)')
+
+
+def cpu_misc_baselines():
+    """C2, C3, C5, C6 of BASELINE.md on one core (the reference's per-sample / per-knot Python loops), small bounded samples."""
+    from types import SimpleNamespace
+    from cacto_b200.conf import get_conf
+    from oracle import per as oper, rtg as ortg, systems as osys
+    out = {}
+    conf = get_conf(SYSTEM)
+    env = osys.make_env(conf)
+    rng = np.random.default_rng(0)
+    n = 128
+    s = rng.uniform(conf.x_init_min, conf.x_init_max, (n, conf.nb_state)).astype(np.float32)
+    a = rng.uniform(conf.u_min, conf.u_max, (n, conf.nb_action)).astype(np.float32)
+    w = np.tile(np.asarray(conf.cost_weights_running, float), (n, 1))
+    for name, fn in (('simulate_batch', lambda: env.simulate_batch(s, a)), ('derivative_batch', lambda: env.derivative_batch(s, a)),
+                     ('reward_batch', lambda: env.reward_batch(w, s, a))):
+        t0 = time.perf_counter(); fn(); out['C2_' + name + '_samples_per_s'] = n / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for i in range(32):
+        env.augmented_derivative(s[i].astype(np.float64), a[i].astype(np.float64))
+    out['C3_augmented_derivative_samples_per_s'] = 32 / (time.perf_counter() - t0)
+    ns = conf.nb_state
+    for B in (64, 4096):
+        bc = SimpleNamespace(REPLAY_SIZE=2 ** 16, BATCH_SIZE=B, nb_state=ns, prioritized_replay_alpha=0.6, prioritized_replay_beta=0.6,
+                             prioritized_replay_eps=1e-2, fresh_factor=0.95)
+        ob = oper.PrioritizedReplayBuffer(bc)
+        rows = rng.normal(size=(8192, 3 * ns + 3))
+        cols = (rows[:, :ns], rows[:, ns], rows[:, ns + 1:2 * ns + 1], rows[:, 2 * ns + 1:3 * ns + 1], rows[:, 3 * ns + 1], rows[:, 3 * ns + 2])
+        ob.add(*[(c,) for c in cols])
+        rtg_, V_ = rng.normal(size=(B, 1)).astype(np.float32), rng.normal(size=(B, 1)).astype(np.float32)
+        reps = 20 if B == 64 else 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            o = ob.sample()
+            ob.update_priorities(o[7], rtg_, V_)
+        out[f'C5_per_rounds_per_s_B{B}'] = reps / (time.perf_counter() - t0)
+    st, c = rng.normal(size=(101, ns)), rng.uniform(0, 2, 101)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ortg.rl_solve(conf, st, c)
+    out['C6_rl_solve_trajectories_per_s'] = 20 / (time.perf_counter() - t0)
+    out['cores'] = 1
+    out['note'] = ('oracle restatements with the reference\'s per-sample / per-knot Python structure (environment.py:134-144, TO.py:181, '
+                   'replay_buffer.py + segment_tree.py, RL.py:173-187), manipulator, capacity-2^16 trees')
+    return out
 
 
 def run_reference(args):
@@ -156,6 +266,20 @@ def run_b200(args):
                'sample': f'{cores * per_core} rollouts x 100 steps ({steps} env-steps, {dt:.1f} s): oracle restatement of RL.py:221-231 '
                          f'(B=1 torch-CPU actor forward + NumPy fp64 RNEA dynamics per step; slower than Pinocchio C++ would be) over '
                          f'multiprocessing.Pool({cores})'}
+        if not args.quick:         # BASELINE.md C4 (update) and C2 / C3 / C5 / C6 one-liners, ~15 s together
+            try:
+                r64, s64 = cpu_update_baseline(SYSTEM, 64, cores, n=3)
+                r16, s16 = cpu_update_baseline(SYSTEM, 16384, cores, n=1, dyn_sample=128)
+                cpu_update = {'64': {'value': r64, 'unit': 'updates/s', 'cores': cores, 'kind': 'port', 'sample': s64},
+                              '16384': {'value': r16, 'unit': 'updates/s', 'cores': cores, 'kind': 'port', 'sample': s16}}
+            except Exception as exc:
+                cpu_update = {'error': f'{type(exc).__name__}: {exc}'}
+            try:
+                cpu_misc = cpu_misc_baselines()
+            except Exception as exc:
+                cpu_misc = {'error': f'{type(exc).__name__}: {exc}'}
+            cpu['update'] = cpu_update
+            cpu['misc'] = cpu_misc
 
     import torch
     import torch.distributed as dist
@@ -257,79 +381,148 @@ def run_b200(args):
     h2d = ics_host.numel() * 8 + B * 4
     d2h = (st_host.numel() + ct_host.numel()) * 8 + fl_host.numel() * 4
 
-    # ---- K3 updates/s (secondary metric): conf batch per GPU, data resident, gradients summed across GPUs inside the Adam kernels
-    Bu = conf.BATCH_SIZE
-    g = torch.Generator(device='cpu').manual_seed(rank)
-    lo, hi = torch.as_tensor(conf.x_init_min), torch.as_tensor(conf.x_init_max)
-    s = (lo + (hi - lo) * torch.rand((Bu, ns), generator=g, dtype=torch.float64)).float().to(dev)
-    sn = (lo + (hi - lo) * torch.rand((Bu, ns), generator=g, dtype=torch.float64)).float().to(dev)
-    pr = (-5 * torch.rand((Bu, 1), generator=g)).to(dev)
-    dv = torch.randn((Bu, ns), generator=g).to(dev); dv[:, -1] = 0
-    d = (torch.rand((Bu, 1), generator=g) < 0.5).float().to(dev)
-    term = (torch.rand((Bu, 1), generator=g) < 0.01).double().to(dev)
-    w = torch.ones((Bu, 1), device=dev)
+    # ---- K3 Sobolev critic+actor updates/s (the second half of the metric): data resident, gradients summed across GPUs inside
+    # the Adam kernels.  Legs: the reference's conf batch (64 per GPU, fp32-FMA tile kernels, latency-bound) and the BASELINE
+    # config 2 / 3 batches (4096, 16384: tcgen05 engine from B = 3072); UR5 (config 5) with its global batches split over the ranks.
+    from cacto_b200.replay_buffer import ReplayBuffer
 
-    def update_step():
-        rl.update(s, sn, pr, dv, d, term, w, fuse_target=True)
-    n_up = 200
-    for _ in range(20):
-        update_step()
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(n_up):
-        update_step()
-    b.record(stream)
-    torch.cuda.synchronize()
-    updates_per_s = n_up / (max_over_ranks(a.elapsed_time(b)) * 1e-3)
-    # the same update replayed as a CUDA graph (6 kernel nodes; data-parallel: the gradient exchange happens inside the two
-    # Adam nodes over NVLink peer memory, so the graph holds no collective)
-    graph_updates_per_s, n_gr = None, 1000
-    if world == 1 or rl._peer is not None:
+    def update_leg(system, B_local, n_eager, n_graph, e2e_updates=0):
+        cf = get_conf(system, BATCH_SIZE=B_local)
+        ev_ = genv.make_env(cf)
+        nn_ = NN(ev_, cf, 1e-2, seed=0)
+        r_ = RL_AC(ev_, nn_, cf, 0, dist=dist if world > 1 else None)
+        r_.setup_model()
+        bt = [torch.as_tensor(x).to(dev) for x in _update_batch(cf, B_local, 7 + rank)]
+        s_, pr_, sn_, dv_, d_, term_, w_ = bt
+        r_.peer_barrier()
+        for _ in range(5):
+            r_.update(s_, sn_, pr_, dv_, d_, term_, w_, fuse_target=True, synced=True)
+        barrier()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(stream)
+        for _ in range(n_eager):
+            r_.update(s_, sn_, pr_, dv_, d_, term_, w_, fuse_target=True, synced=True)
+        b_.record(stream)
+        torch.cuda.synchronize()
+        eager_us = max_over_ranks(a_.elapsed_time(b_)) * 1e3 / n_eager
+        graph_us = None
+        if world == 1 or r_._peer is not None:
+            try:
+                ug = r_.make_update_graph(B_local)
+                for k_, t_ in (('state', s_), ('state_next', sn_), ('partial_rtg', pr_), ('dVdx', dv_), ('done', d_), ('term', term_), ('weights', w_)):
+                    ug.io[k_].copy_(t_)
+                for _ in range(10):
+                    ug.replay()
+                barrier()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(stream)
+                for _ in range(n_graph):
+                    ug.replay()
+                b_.record(stream)
+                torch.cuda.synchronize()
+                graph_us = max_over_ranks(a_.elapsed_time(b_)) * 1e3 / n_graph
+                del ug
+            except Exception as exc:           # report, do not hide
+                graph_us = f'failed: {type(exc).__name__}: {exc}'
+        best_us = graph_us if isinstance(graph_us, float) else eager_us
+        ns_, na_ = cf.nb_state, cf.nb_action
+        P_c, P_a = 64 * ns_ + 28800, 256 * ns_ + 65536 + 256 * na_
+        flops = 2.0 * B_local * (10 * P_c + 3 * P_a)                 # MACs ~ B (10 P_c + 3 P_a)
+        ach = flops / (best_us * 1e-6) / 1e12
+        tc = nn_._use_tc(B_local)
+        leg = {'system': system, 'batch_per_gpu': B_local, 'global_batch': B_local * world, 'engine': 'tcgen05 (update_tc.cu)' if tc else 'fp32 FMA (update.cu)',
+               'us_per_update_eager': eager_us, 'us_per_update_cuda_graph': graph_us, 'updates_per_s': 1e6 / best_us,
+               'samples_per_s': B_local * world * 1e6 / best_us, 'algorithmic_flops_per_update': flops}
+        if tc:
+            leg['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': ach / bf16_peak,
+                               'ceiling_3xfp16': bf16_peak / 3.0, 'frac_of_3xfp16_ceiling': ach / (bf16_peak / 3.0), 'peak_source': peak_src,
+                               'note': 'layer-wise sweeps over 128-sample tiles; the sweeps are bound by workspace traffic (~10 KB per sample '
+                                       'through L2/HBM) and CUDA-core epilogues, not by the tensor pipe (profiles/README.md)'}
+        else:
+            leg['roofline'] = {'bound': 'fp32_fma' if B_local >= 1024 else 'latency', 'achieved': ach, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
+                               'frac': ach / fma_peak_tflops, 'peak_source': 'cacto_peak_fma_fp32 measured in this run'}
+        if e2e_updates:
+            # end to end through the public API, as RL_AC.learn_and_update runs it (RL.py:120-143): ReplayBuffer.sample() draws the
+            # indices on the host (np.random, quirk Q5), ships them, gathers the rows; update; the loss is read back every update
+            buf = ReplayBuffer(cf)
+            rows = torch.randn((cf.REPLAY_SIZE + 8, 3 * ns_ + 3), dtype=torch.float64, device=dev)      # wraps: the buffer reports full
+            rows[:, :ns_] = s_.double()[torch.randint(0, B_local, (cf.REPLAY_SIZE + 8,), device=dev)]
+            rows[:, ns_ + 1:2 * ns_ + 1] = rows[:, :ns_]
+            rows[:, 3 * ns_ + 1] = (rows[:, 3 * ns_ + 1] > 0).double()
+            rows[:, 3 * ns_ + 2] = (rows[:, 3 * ns_ + 2] > 2.3).double()
+            buf.add_rows(rows)
+            np.random.seed(0)
+            g_ = getattr(r_, 'update_graph', None)
+            r_.peer_barrier()
+            for it in range(3 + e2e_updates):
+                if it == 3:
+                    torch.cuda.synchronize()
+                    t0_ = time.perf_counter()
+                bs = buf.sample()
+                r_.update(bs[0], bs[2], bs[1], bs[3], bs[4], bs[5], bs[6], fuse_target=True, synced=True)
+                loss_host = float(nn_.last_critic_loss)          # device -> host read of the step's result
+            e2e_s_ = max_over_ranks(time.perf_counter() - t0_)
+            leg['e2e'] = {'value': e2e_updates / e2e_s_, 'unit': 'updates/s', 'h2d_bytes_per_step': 8 * B_local, 'd2h_bytes_per_step': 4,
+                          'note': 'ReplayBuffer.sample (host index draw + device gather) + RL_AC.update (eager launches) + loss read-back per update; '
+                                  f'last loss {loss_host:.4g}'}
+        del r_, nn_
+        return leg
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    bf16_peak = peaks.get('bf16_tflops') or 1590.0
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks.get('bf16_tflops') else 'fallback 1590 TFLOP/s'
+    upd_legs = [update_leg(SYSTEM, conf.BATCH_SIZE, 200, 1000, e2e_updates=200)]
+    if not args.quick:
+        upd_legs.append(update_leg(SYSTEM, 4096, 30, 100))
+        upd_legs.append(update_leg(SYSTEM, 16384, 20, 50, e2e_updates=30))
+        for Bg in (64, 4096, 16384):                  # BASELINE config 5: UR5, global batch split over the ranks
+            if Bg % world == 0:
+                upd_legs.append(update_leg('ur5', Bg // world, 20 if Bg > 64 else 100, 50 if Bg > 64 else 300))
+    Bu = conf.BATCH_SIZE
+    updates_per_s = 1e6 / upd_legs[0]['us_per_update_eager']
+    graph_us0 = upd_legs[0]['us_per_update_cuda_graph']
+    graph_updates_per_s = 1e6 / graph_us0 if isinstance(graph_us0, float) else graph_us0
+
+    # data-parallel correctness, visible to the driver: one update from identical weights through the NVLink peer-memory exchange and
+    # through NCCL all-reduces must agree (1e-4, the parity gate), and the replicas must stay bit-identical
+    dp_check = None
+    if world > 1:
         try:
-            ug = rl.make_update_graph(Bu)
-            for k_, t_ in (('state', s), ('state_next', sn), ('partial_rtg', pr), ('dVdx', dv), ('done', d), ('term', term), ('weights', w)):
-                ug.io[k_].copy_(t_)
-            for _ in range(20):
-                ug.replay()
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(n_gr):
-                ug.replay()
-            b.record(stream)
+            ra = RL_AC(env, NN(env, conf, 1e-2, seed=0), conf, 0, dist=dist)
+            ra.setup_model()
+            rb = RL_AC(env, NN(env, conf, 1e-2, seed=0), conf, 0, dist=dist, reduce='nccl')
+            rb.setup_model()
+            for na_, nb_ in ((ra.actor_model, rb.actor_model), (ra.critic_model, rb.critic_model), (ra.target_critic, rb.target_critic)):
+                nb_.params.copy_(na_.params)
+                nb_.refresh_transposed()
+            bt = [torch.as_tensor(x).to(dev) for x in _update_batch(conf, Bu, 100 + rank)]
+            s_, pr_, sn_, dv_, d_, term_, w_ = bt
+            for r_ in (ra, rb):
+                for _ in range(2):
+                    r_.update(s_, sn_, pr_, dv_, d_, term_, w_, fuse_target=True)
             torch.cuda.synchronize()
-            graph_ms = a.elapsed_time(b)
-            del ug
-        except Exception as exc:           # report, do not hide
-            graph_ms, graph_updates_per_s = -1.0, f'failed: {type(exc).__name__}: {exc}'
-        graph_ms_all = max_over_ranks(graph_ms)
-        if graph_ms > 0:
-            graph_updates_per_s = n_gr / (graph_ms_all * 1e-3)
-    # the update at the batch sizes of BASELINE configs 2 / 3 (PER batch 4096, critic batch 16384), single GPU, eager launches
-    large_batch = {}
-    if world == 1:
-        for Bl in (4096, 16384):
-            gl = torch.Generator(device='cpu').manual_seed(Bl)
-            sl = (lo + (hi - lo) * torch.rand((Bl, ns), generator=gl, dtype=torch.float64)).float().to(dev)
-            snl = (lo + (hi - lo) * torch.rand((Bl, ns), generator=gl, dtype=torch.float64)).float().to(dev)
-            prl = (-5 * torch.rand((Bl, 1), generator=gl)).to(dev)
-            dvl = torch.randn((Bl, ns), generator=gl).to(dev); dvl[:, -1] = 0
-            dl = (torch.rand((Bl, 1), generator=gl) < 0.5).float().to(dev)
-            tl = (torch.rand((Bl, 1), generator=gl) < 0.01).double().to(dev)
-            wl = torch.ones((Bl, 1), device=dev)
-            for _ in range(5):
-                rl.update(sl, snl, prl, dvl, dl, tl, wl, fuse_target=True)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(30):
-                rl.update(sl, snl, prl, dvl, dl, tl, wl, fuse_target=True)
-            b.record(stream)
-            torch.cuda.synchronize()
-            us = a.elapsed_time(b) * 1e3 / 30
-            large_batch[str(Bl)] = {'us_per_update': us, 'samples_per_s': Bl / (us * 1e-6),
-                                    'algorithmic_tflops': Bl * 0.994e6 / (us * 1e-6) / 1e12}
+            worst = 0.0
+            for na_, nb_ in ((ra.actor_model, rb.actor_model), (ra.critic_model, rb.critic_model), (ra.target_critic, rb.target_critic)):
+                worst = max(worst, float((na_.params - nb_.params).abs().max() / nb_.params.abs().max()))
+            gathered = [torch.empty_like(ra.actor_model.params) for _ in range(world)]
+            dist.all_gather(gathered, ra.actor_model.params)
+            identical = all(bool(torch.equal(gathered[0], g_)) for g_ in gathered[1:])
+            ok = worst <= 1e-4 and identical
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            exch = 'peer' if ra._peer is not None else 'nccl (peer unavailable)'
+            dp_check = ('ok' if int(flag[0]) == 1 else 'FAILED') + f': {exch} vs nccl max rel diff {worst:.2e} after 2 updates, replicas bit-identical: {identical}'
+            del ra, rb
+        except Exception as exc:
+            dp_check = f'FAILED: {type(exc).__name__}: {exc}'
+    large_batch = {str(l['batch_per_gpu']): {'us_per_update': l['us_per_update_eager'], 'us_per_update_cuda_graph': l['us_per_update_cuda_graph'],
+                                              'samples_per_s': l['samples_per_s'], 'engine': l['engine'],
+                                              'algorithmic_tflops': l['roofline']['achieved']}
+                   for l in upd_legs if l['system'] == SYSTEM and l['batch_per_gpu'] > 64}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -342,7 +535,7 @@ def run_b200(args):
         peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks.get('bf16_tflops') else 'fallback 1590 TFLOP/s'
         if args.engine == 'tc':
             roof = {'bound': 'tensor', 'achieved': achieved_tflops, 'peak': bf16, 'unit': 'TFLOP/s', 'frac': achieved_tflops / bf16,
-                    'traffic': TRAFFIC_BYTES.get(args.engine), 'peak_source': peak_src,
+                    'traffic': TRAFFIC_BYTES.get(args.engine), 'traffic_source': TRAFFIC_SOURCE.get(args.engine), 'peak_source': peak_src,
                     'ceiling_3xfp16': bf16 / 3.0, 'frac_of_3xfp16_ceiling': achieved_tflops / (bf16 / 3.0),
                     'note': 'k_rollout_tc16: 256x256 actor layer on tcgen05.mma kind::f16 with fp16 hi/lo operand splitting (3 UMMAs per logical '
                             'product, fp32 accumulation in TMEM, fp32-class accuracy: parity gate 1e-5), persistent CTAs with two free-running '
@@ -377,7 +570,16 @@ def run_b200(args):
                             'while sub-batch k+1 is rolled out; PCIe-bound (1.06 GB per step)'},
             'gpu_launches': K * launches_per_step,          # device-resident leg; the e2e leg launches 2 + 8 kernels per step
             'clocks': clocks,
-            'extra': {'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s,
+            'extra': {'update': {'metric': 'Sobolev actor-critic updates/s (RL_AC.update: critic gradient, Adam + Polyak, actor gradient, Adam)',
+                                 'legs': upd_legs, 'dp_check': dp_check,
+                                 'cpu_baseline': (cpu or {}).get('update'),
+                                 'note': 'updates_per_s = CUDA-graph replay where capture is possible, else eager; value of a leg counts updates of '
+                                         'the GLOBAL batch (all ranks step together); roofline.achieved = algorithmic flops 2 B (10 P_c + 3 P_a) / time'},
+                      'cpu_baselines_C2_C6': (cpu or {}).get('misc'),
+                      'parity': 'oracle pinned by reference-executed goldens for PER / reward-to-go / analytic systems / rewards / SI-car-car_park '
+                                'backward pass; UNPINNED for pinocchio-backed dynamics and tensorflow update semantics (absent here): '
+                                'tests/golden/make_golden_ext.py is the kit that pins them where the wheels exist',
+                      'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s,
                       'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world, 'update_kernels_per_update': 6,
                       'update_gradient_exchange': ('none (1 GPU)' if world == 1 else
                                                    'NVLink peer-memory sum inside the Adam kernels (k_adam_peer)' if rl._peer is not None else
@@ -417,6 +619,7 @@ def main():
     ap.add_argument('--engine', default='tc', choices=['tc', 'tf32', 'fma'])
     ap.add_argument('--rollouts-per-gpu', type=int, default=ROLLOUTS_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='rollout legs and the conf-batch update only')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -219,7 +219,7 @@ class NN:
     # -- gradient launches (shared by the eager methods below and by RL_AC's CUDA-graph update) -----------
     # Batch size from which the 'sine' critic / actor gradients run on the tensor-core kernels (csrc/update_tc.cu: 128-sample
     # tiles, one tile per SM) instead of the fused fp32-FMA tile kernels (csrc/update.cu).  ``update_engine``: 'auto' | 'fma' | 'tc'.
-    TC_MIN_BATCH = 2048
+    TC_MIN_BATCH = 3072
     update_engine = 'auto'
 
     def _use_tc(self, B):

@@ -128,7 +128,16 @@ __global__ void __launch_bounds__(512) k_tc_prepare(const PrepTable T) {
     for (int i = tid; i < T.nzero; i += 512) T.zero[i] = 0u;
   // every CTA of a job scans the whole matrix for max|W| (L2-resident, <= 64 K floats)
   uint32_t m = 0;
-  for (int i = tid; i < J.in * J.out; i += 512) m = max(m, __float_as_uint(__ldg(J.W + i)) & 0x7fffffffu);
+  {
+    const int n4 = (J.in * J.out) >> 2;                      // every layer block starts 16-byte aligned and holds a multiple of 4 floats ...
+    const float4* w4 = reinterpret_cast<const float4*>(J.W);
+#pragma unroll 8
+    for (int i = tid; i < n4; i += 512) {
+      const float4 w = __ldg(w4 + i);
+      m = max(max(m, __float_as_uint(w.x) & 0x7fffffffu), max(__float_as_uint(w.y) & 0x7fffffffu, max(__float_as_uint(w.z) & 0x7fffffffu, __float_as_uint(w.w) & 0x7fffffffu)));
+    }
+    for (int i = 4 * n4 + tid; i < J.in * J.out; i += 512) m = max(m, __float_as_uint(__ldg(J.W + i)) & 0x7fffffffu);   // ... except actor W3 with odd na
+  }
   m = __reduce_max_sync(0xffffffffu, m);
   if ((tid & 31) == 0) wmax[tid >> 5] = m;
   __syncthreads();
