@@ -88,3 +88,46 @@ def test_tc_entry_points_validate_arguments():
     assert lib.cacto_actor_grad_tc(nn._p, ptr(am.params), ptr(cm.params), ptr(z), ptr(t), 1.0, ptr(am.grad), None, 256, None, need, None) == -1
     assert lib.cacto_actor_grad_tc(nn._p, ptr(am.params), ptr(cm.params), ptr(z), ptr(t), 1.0, ptr(am.grad), None, -1, ptr(ws), need, None) == -4
     assert lib.cacto_actor_grad_tc(nn._p, ptr(am.params), ptr(cm.params), ptr(z), ptr(t), 1.0, ptr(am.grad), None, 0, ptr(ws), need, None) == 0
+
+
+def test_tc_kernels_stay_inside_their_buffers():
+    """compute-sanitizer is closed on the GPU pool (profiles/r2_sanitizer_closed.txt), so the bounds of the tensor-core update are
+    checked directly: workspace, gradient blocks and per-row outputs sit between canary bands that must survive a ragged-batch
+    update (the last 128-row tile is partial: B = 130), and the outputs must be fully written."""
+    from cacto_b200._lib import check, lib, ptr
+    conf, env, nn, rl, batch = make('manipulator', 130)
+    s, pr, sn, dv, d, term, w = [torch.as_tensor(x, device='cuda') for x in batch]
+    B, ns, na = 130, conf.nb_state, conf.nb_action
+    need = int(lib.cacto_update_tc_workspace_bytes(B, ns, na))
+    G = 4096                                              # canary bytes on each side (multiple of 256: keeps the alignment)
+    big = torch.full((need + 2 * G,), 0xA5, dtype=torch.uint8, device='cuda')
+    off = (-big.data_ptr()) % 256
+    ws_ptr = big.data_ptr() + off + (G - 256)
+    lo_band, hi_band = big[:off + G - 256].clone(), big[off + G - 256 + need:].clone()
+
+    def guarded(n, dtype=torch.float32):
+        t = torch.full((n + 64,), float('nan'), dtype=dtype, device='cuda')
+        return t, t[32:32 + n]
+    cm, am, tc = rl.critic_model, rl.actor_model, rl.target_critic
+    gc_all, gc = guarded(cm.n)
+    ga_all, ga = guarded(am.n)
+    gc.zero_(); ga.zero_()
+    outs = [guarded(B) for _ in range(3)]
+    act_all, act = guarded(B * na)
+    loss = torch.zeros(1, device='cuda')
+    import ctypes as C
+    check(lib.cacto_critic_grad_tc(nn._p, ptr(cm.params), ptr(tc.params), 1e-2, 0, ptr(s), ptr(sn), ptr(pr.reshape(-1)), ptr(dv), ptr(d.reshape(-1)),
+                                   ptr(w.reshape(-1)), 1.0 / B, ptr(gc), ptr(outs[0][1]), ptr(outs[1][1]), ptr(outs[2][1]), ptr(loss), B,
+                                   C.c_void_p(ws_ptr), need, None), 'critic_grad_tc')
+    check(lib.cacto_actor_grad_tc(nn._p, ptr(am.params), ptr(cm.params), ptr(s), ptr(term.reshape(-1)), 1.0 / B, ptr(ga), ptr(act), B,
+                                  C.c_void_p(ws_ptr), need, None), 'actor_grad_tc')
+    torch.cuda.synchronize()
+    assert torch.equal(big[:off + G - 256], lo_band) and torch.equal(big[off + G - 256 + need:], hi_band), 'workspace canary overwritten'
+    for all_, view in [(gc_all, gc), (ga_all, ga), (act_all, act)] + outs:
+        assert torch.isnan(all_[:32]).all() and torch.isnan(all_[32 + view.numel():]).all(), 'write outside an output buffer'
+        assert torch.isfinite(view).all(), 'output not fully written'
+    # and the results are the engine's results
+    nn.update_engine = 'fma'
+    g_ref = [x.clone() for x in nn.compute_critic_grad(cm, tc, s, sn, pr, dv, d, w)[0]]
+    ref = torch.cat([x.reshape(-1) for x in g_ref])
+    assert float((gc - ref).abs().max()) <= 5e-5 * float(ref.abs().max())
