@@ -24,6 +24,7 @@ import torch
 from . import _lib
 from ._lib import check, lib, ptr, stream_ptr
 from .environment import _as_cuda, _device
+from .ops import ops
 
 CRITIC_HIDDEN = (64, 64, 128, 128)
 
@@ -89,8 +90,7 @@ class Network:
     def refresh_transposed(self):
         if self.params_T is None:
             return
-        check(lib.cacto_transpose_params(ptr(self.params), ptr(self.params_T), self.is_critic, self.ns, self.na, stream_ptr()),
-              'transpose_params')
+        ops.transpose_params(self.params, self.params_T, self.is_critic, self.ns, self.na)
 
     def save_weights(self, path):
         """Checkpoint as .npz (the reference writes Keras .h5, RL.py:191-195; .h5 export is listed as next work)."""
@@ -127,6 +127,7 @@ class NN:
         self.w_S = w_S
         self._rng = np.random.default_rng(seed)
         self._p = env._p
+        self._pt = env._pt
         self.last_critic_loss = torch.zeros(1, dtype=torch.float32, device=_device())
 
     # -- model constructors ---------------------------------------------------------------------
@@ -193,14 +194,14 @@ class NN:
         B = x.shape[0]
         if NN.kind == 'actor':
             out = torch.empty((B, NN.na), dtype=torch.float32, device=x.device)
-            check(lib.cacto_actor_forward(self._p, ptr(NN.params), ptr(x), ptr(out), B, stream_ptr()), 'actor_forward')
+            ops.actor_forward(self._pt, NN.params, x, out)
         elif NN.kind == 'critic_generic':
             out = torch.empty((B, 1), dtype=torch.float32, device=x.device)
             check(lib.cacto_mlp_forward_generic(self._p, _lib.C.byref(NN.desc), ptr(NN.params), ptr(x), ptr(out), ptr(None), B, stream_ptr()),
                   'mlp_forward_generic')
         else:
             out = torch.empty((B, 1), dtype=torch.float32, device=x.device)
-            check(lib.cacto_critic_forward(self._p, ptr(NN.params), ptr(x), ptr(out), ptr(None), B, stream_ptr()), 'critic_forward')
+            ops.critic_forward(self._pt, NN.params, x, out, None)
         return out
 
     def eval_with_gradient(self, critic, input):
@@ -213,7 +214,7 @@ class NN:
             check(lib.cacto_mlp_forward_generic(self._p, _lib.C.byref(critic.desc), ptr(critic.params), ptr(x), ptr(V), ptr(dV), B, stream_ptr()),
                   'mlp_forward_generic')
         else:
-            check(lib.cacto_critic_forward(self._p, ptr(critic.params), ptr(x), ptr(V), ptr(dV), B, stream_ptr()), 'critic_forward')
+            ops.critic_forward(self._pt, critic.params, x, V, dV)
         return V, dV
 
     # -- gradient launches (shared by the eager methods below and by RL_AC's CUDA-graph update) -----------
@@ -229,7 +230,7 @@ class NN:
         return eng == 'tc' or (eng == 'auto' and B >= self.TC_MIN_BATCH)
 
     def _tc_workspace(self, B):
-        need = int(lib.cacto_update_tc_workspace_bytes(B, self.conf.nb_state, self.conf.nb_action))
+        need = int(ops.update_tc_workspace_bytes(B, self.conf.nb_state, self.conf.nb_action))
         ws = getattr(self, '_tc_ws', None)
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=_device())       # cudaMalloc: 256-byte aligned or better; checked by the callee
@@ -239,24 +240,21 @@ class NN:
     def launch_critic_grad(self, cm, tc, s, sn, pr, dv, d, w, inv_B, rtg, V, Vt, B):
         if cm.kind == 'critic_sine' and self._use_tc(B):
             ws = self._tc_workspace(B)
-            check(lib.cacto_critic_grad_tc(self._p, ptr(cm.params), ptr(tc.params), float(self.w_S), int(bool(self.conf.MC)), ptr(s), ptr(sn), ptr(pr),
-                                           ptr(dv), ptr(d), ptr(w), inv_B, ptr(cm.grad), ptr(rtg), ptr(V), ptr(Vt), ptr(self.last_critic_loss), B,
-                                           ptr(ws), ws.numel(), stream_ptr()), 'critic_grad_tc')
+            ops.critic_grad_tc(self._pt, cm.params, tc.params, float(self.w_S), int(bool(self.conf.MC)), s, sn, pr, dv, d, w, inv_B, cm.grad, rtg, V, Vt,
+                               self.last_critic_loss, ws)
             return
         if cm.kind == 'critic_generic':
             check(lib.cacto_critic_grad_generic(self._p, _lib.C.byref(cm.desc), ptr(cm.params), ptr(tc.params), float(self.w_S),
                                                 int(bool(self.conf.MC)), ptr(s), ptr(sn), ptr(pr), ptr(dv), ptr(d), ptr(w), inv_B, ptr(cm.grad),
                                                 ptr(rtg), ptr(V), ptr(Vt), ptr(self.last_critic_loss), B, stream_ptr()), 'critic_grad_generic')
         else:
-            check(lib.cacto_critic_grad(self._p, ptr(cm.params), ptr(cm.params_T), ptr(tc.params), float(self.w_S), int(bool(self.conf.MC)),
-                                        ptr(s), ptr(sn), ptr(pr), ptr(dv), ptr(d), ptr(w), inv_B, ptr(cm.grad), ptr(rtg), ptr(V), ptr(Vt),
-                                        ptr(self.last_critic_loss), B, stream_ptr()), 'critic_grad')
+            ops.critic_grad(self._pt, cm.params, cm.params_T, tc.params, float(self.w_S), int(bool(self.conf.MC)), s, sn, pr, dv, d, w, inv_B, cm.grad, rtg, V, Vt,
+                            self.last_critic_loss)
 
     def launch_actor_grad(self, am, cm, s, term, inv_B, actions, B):
         if cm.kind == 'critic_sine' and self._use_tc(B):
             ws = self._tc_workspace(B)
-            check(lib.cacto_actor_grad_tc(self._p, ptr(am.params), ptr(cm.params), ptr(s), ptr(term), inv_B, ptr(am.grad), ptr(actions), B,
-                                          ptr(ws), ws.numel(), stream_ptr()), 'actor_grad_tc')
+            ops.actor_grad_tc(self._pt, am.params, cm.params, s, term, inv_B, am.grad, actions, ws)
             return
         if cm.kind == 'critic_generic':
             # environment terms from the batched kernels of the reference-facing API (NeuralNetwork.py:185-204), network part generic
@@ -278,8 +276,7 @@ class NN:
             check(lib.cacto_actor_grad_generic(self._p, _lib.C.byref(am.desc), ptr(am.params), _lib.C.byref(cm.desc), ptr(cm.params), ptr(s),
                                                ptr(s_next), ptr(Fu), ptr(dr_da), inv_B, ptr(am.grad), B, stream_ptr()), 'actor_grad_generic')
         else:
-            check(lib.cacto_actor_grad(self._p, ptr(am.params), ptr(am.params_T), ptr(cm.params), ptr(cm.params_T), ptr(s), ptr(term), inv_B,
-                                       ptr(am.grad), ptr(actions), B, stream_ptr()), 'actor_grad')
+            ops.actor_grad(self._pt, am.params, am.params_T, cm.params, cm.params_T, s, term, inv_B, am.grad, actions)
 
     def custom_logarithm(self, input):
         """NeuralNetwork.py:140-148."""

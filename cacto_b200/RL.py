@@ -18,6 +18,7 @@ import torch
 
 from ._lib import check, lib, ptr, stream_ptr
 from .environment import _as_cuda, _device
+from .ops import ops
 from .optim import Adam, PiecewiseConstantDecay
 from .parallel import PeerReduce, PeerRegion, PeerUnavailable, allreduce_sum
 from .rtg import rtg_batch as _rtg_batch
@@ -258,9 +259,12 @@ class RL_AC:
                 img = torch.empty(int(lib.cacto_actor_tc16_image_bytes()), dtype=torch.uint8, device=am.params.device)
                 self._w2img16 = img
             if prepare:          # the W2 image follows the policy version; sub-batches of one call share it
-                check(lib.cacto_actor_tc16_prepare(ptr(am.params), am.ns, am.na, ptr(img), stream_ptr()), 'actor_tc16_prepare')
-            check(lib.cacto_rollout_tc16(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
-                                         ptr(rewards), B, stream_ptr()), 'rollout_tc16')
+                ops.actor_tc16_prepare(am.params, am.ns, am.na, img)
+            if states.is_cuda:
+                ops.rollout_tc16(self.env._pt, am.params, img, ics, hz, T_max, states, controls, flags, rewards)
+            else:                # zero-copy mode: the outputs are pinned HOST buffers addressed through UVA (no torch CUDA tensor): plain C ABI
+                check(lib.cacto_rollout_tc16(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
+                                             ptr(rewards), B, stream_ptr()), 'rollout_tc16')
         elif use_actor and engine == 'tc2':
             img = getattr(self, '_w2img16p', None)
             if img is None:
@@ -280,9 +284,11 @@ class RL_AC:
             check(lib.cacto_rollout_tc(self.env._p, ptr(am.params), ptr(img), ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
                                        ptr(rewards), B, stream_ptr()), 'rollout_tc')
         else:
-            actor = am.params if use_actor else None
-            check(lib.cacto_rollout(self.env._p, ptr(actor), use_actor, ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls), ptr(flags),
-                                    ptr(rewards), B, stream_ptr()), 'rollout')
+            if states.is_cuda:
+                ops.rollout(self.env._pt, am.params if use_actor else None, use_actor, ics, hz, T_max, states, controls, flags, rewards)
+            else:
+                check(lib.cacto_rollout(self.env._p, ptr(am.params if use_actor else None), use_actor, ptr(ics), ptr(hz), T_max, ptr(states), ptr(controls),
+                                        ptr(flags), ptr(rewards), B, stream_ptr()), 'rollout')
 
     def rollout_batch(self, ICS, ep, horizon=None, with_reward=False, engine=None):
         """All warm-starts of RL.py:197-233 for ICS[B, ns] in one launch of the fused actor+dynamics kernel.

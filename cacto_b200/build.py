@@ -1,4 +1,5 @@
-"""Build libcacto_b200.so in-tree with nvcc for sm_100a (one object per .cu, compiled in parallel)."""
+"""Build libcacto_b200.so in-tree with nvcc for sm_100a (one object per .cu, compiled in parallel) and the PyTorch custom-op shim
+libcacto_b200_torch.so (csrc/torch_ops.cpp: TORCH_LIBRARY(cacto, ...) over the C ABI) with g++ against the installed torch."""
 import os
 import subprocess
 import sys
@@ -8,6 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libcacto_b200.so')
+OUT_TORCH = os.path.join(HERE, 'libcacto_b200_torch.so')
+CXX = os.environ.get('CXX', 'g++')
 BUILD = os.path.join(ROOT, 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
@@ -48,7 +51,30 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     if force or jobs or _stale(OUT, objs):
         run([NVCC] + ARCH + ['-shared', '-o', OUT] + objs)
+    build_torch_ops(force=force, run=run)
     return OUT
+
+
+def build_torch_ops(force=False, run=None):
+    """csrc/torch_ops.cpp -> libcacto_b200_torch.so, linked against libcacto_b200.so (rpath $ORIGIN) and libtorch."""
+    import torch
+    src = os.path.join(CSRC, 'torch_ops.cpp')
+    hdr = os.path.join(ROOT, 'include', 'cacto_b200.h')
+    if not (force or _stale(OUT_TORCH, [src, hdr, OUT])):
+        return OUT_TORCH
+    ti = os.path.dirname(torch.__file__)
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    cmd = [CXX, '-O2', '-std=c++17', '-fPIC', '-shared', '-D_GLIBCXX_USE_CXX11_ABI=%d' % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           '-I' + os.path.join(ROOT, 'include'), '-I' + os.path.join(ti, 'include'), '-I' + os.path.join(ti, 'include', 'torch', 'csrc', 'api', 'include'),
+           '-I' + cuda_inc, src, '-o', OUT_TORCH, '-L' + HERE, '-lcacto_b200', '-L' + os.path.join(ti, 'lib'), '-lc10', '-lc10_cuda', '-ltorch_cpu', '-ltorch',
+           '-Wl,-rpath,$ORIGIN', '-Wl,-rpath,' + os.path.join(ti, 'lib')]
+    if run is None:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('torch ops build failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
+    else:
+        run(cmd)
+    return OUT_TORCH
 
 
 if __name__ == '__main__':

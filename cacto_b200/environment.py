@@ -24,6 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib, ptr, stream_ptr
+from .ops import ops, sys_tensor
 
 _DT = {torch.float32: 0, torch.float64: 1}
 
@@ -64,7 +65,8 @@ class Env:
             (self.XC1, self.YC1, self.XC2, self.YC2, self.XC3, self.YC3,
              self.A1, self.B1, self.A2, self.B2, self.A3, self.B3) = [o[i] for i in range(12)]
         self.params = _lib.make_sys_params(conf)
-        self._p = C.byref(self.params)
+        self._p = C.byref(self.params)                 # for the entry points still bound with ctypes
+        self._pt = sys_tensor(self.params)             # for the torch.ops.cacto.* custom ops
         self.ns = int(conf.nb_state)
         self.na = int(conf.nb_action)
 
@@ -110,15 +112,14 @@ class Env:
         """environment.py:134-138 -> [B, ns]."""
         s, a = self._sa(state, action)
         out = torch.empty_like(s)
-        check(lib.cacto_dyn_step(self._p, _DT[s.dtype], 0, ptr(s), ptr(a), ptr(out), s.shape[0], stream_ptr()), 'dyn_step')
+        ops.dyn_step(self._pt, 0, s, a, out)
         return out
 
     def derivative_batch(self, state, action):
         """environment.py:140-144 -> [B, ns, na] (normalised, zero time row)."""
         s, a = self._sa(state, action)
         out = torch.empty((s.shape[0], self.ns, self.na), dtype=s.dtype, device=s.device)
-        check(lib.cacto_dyn_derivative(self._p, _DT[s.dtype], 0, ptr(s), ptr(a), ptr(out), s.shape[0], stream_ptr()),
-              'dyn_derivative')
+        ops.dyn_derivative(self._pt, 0, s, a, out)
         return out
 
     def augmented_derivative_batch(self, state, action):
@@ -130,14 +131,13 @@ class Env:
         B = s.shape[0]
         Fx = torch.empty((B, self.nx, self.nx), dtype=s.dtype, device=s.device)
         Fu = torch.empty((B, self.nx, self.na), dtype=s.dtype, device=s.device)
-        check(lib.cacto_dyn_augmented(self._p, _DT[s.dtype], 0, ptr(s), ptr(a), ptr(Fx), ptr(Fu), B, stream_ptr()),
-              'dyn_augmented')
+        ops.dyn_augmented(self._pt, 0, s, a, Fx, Fu)
         return Fx, Fu
 
     def get_end_effector_position_batch(self, state):
         s = _as_cuda(state)
         out = torch.empty((s.shape[0], 3), dtype=s.dtype, device=s.device)
-        check(lib.cacto_ee_position(self._p, _DT[s.dtype], 0, ptr(s), ptr(out), s.shape[0], stream_ptr()), 'ee_position')
+        ops.ee_position(self._pt, 0, s.contiguous(), out)
         return out
 
     def _weights8(self, weights, B):
@@ -154,8 +154,7 @@ class Env:
                          and weights.dtype == torch.float64) else self._weights8(weights, B)
         r = torch.empty((B,), dtype=s.dtype, device=s.device)
         g = torch.empty((B, self.na), dtype=s.dtype, device=s.device) if want_grad else None
-        check(lib.cacto_reward(self._p, _DT[s.dtype], 0, ptr(w8), ptr(s), ptr(a), int(plain_ucost), ptr(r), ptr(g), B,
-                               stream_ptr()), 'reward')
+        ops.reward(self._pt, 0, w8.contiguous(), s, a, int(plain_ucost), r, g)
         return r, g
 
     def reward_batch(self, weights, state, action):

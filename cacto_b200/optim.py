@@ -13,6 +13,7 @@ import torch
 
 from ._lib import check, lib, ptr, stream_ptr
 from .NeuralNetwork import Network
+from .ops import ops
 
 
 class PiecewiseConstantDecay:
@@ -61,8 +62,7 @@ class Adam:
         """Launch the schedule kernel: alpha_t for the coming step, step counter += 1, ``zero[0] = 0``
         (an optional one-element float tensor, e.g. the loss accumulator the next kernel adds into)."""
         d = self._device_state(device)
-        check(lib.cacto_adam_schedule(ptr(d['step']), ptr(d['boundaries']), ptr(d['values']), d['nb'], self.beta_1, self.beta_2,
-                                      ptr(d['alpha']), ptr(zero), stream_ptr()), 'adam_schedule')
+        ops.adam_schedule(d['step'], d['boundaries'], d['values'], d['nb'], self.beta_1, self.beta_2, d['alpha'], zero)
 
     def step(self, net, target=None, tau=0.0, prepared=False, peer=None, zero_other=None):
         """One Adam step on ``net`` from ``net.grad`` (zeroed afterwards); optionally the Polyak update
@@ -83,9 +83,8 @@ class Adam:
                                            self.beta_2, self.epsilon, tgt, float(tau), ptr(net.params_T), net.is_critic, net.ns, net.na, net.n,
                                            max_ctas, stream_ptr()), 'adam_step_peer')
         else:
-            check(lib.cacto_adam_step(ptr(net.params), ptr(net.grad), ptr(m), ptr(v), 0.0, ptr(d['alpha']), self.beta_1, self.beta_2,
-                                      self.epsilon, tgt, float(tau), ptr(net.params_T), net.is_critic, net.ns, net.na, net.n, stream_ptr()),
-                  'adam_step')
+            ops.adam_step(net.params, net.grad, m, v, 0.0, d['alpha'], self.beta_1, self.beta_2, self.epsilon, target.params if target is not None else None,
+                          float(tau), net.params_T, net.is_critic, net.ns, net.na)
         self.iterations += 1
 
     def apply_gradients(self, grads_and_vars):

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from ._lib import check, lib, ptr, stream_ptr
+from .ops import ops
 from .segment_tree import MinSegmentTree, SumSegmentTree, _dev
 
 
@@ -78,8 +79,7 @@ class ReplayBuffer(object):
             s, r, s1, dv, d = (torch.empty((n, ns), **f32), torch.empty((n, 1), **f32), torch.empty((n, ns), **f32),
                                torch.empty((n, ns), **f32), torch.empty((n, 1), **f32))
             term = torch.empty((n, 1), dtype=torch.float64, device=dev)
-        check(lib.cacto_buffer_gather(ptr(self.storage_mat), ns, ptr(idx_dev), n, ptr(s), ptr(r), ptr(s1), ptr(dv), ptr(d),
-                                      ptr(term), ptr(None), ptr(None), stream_ptr()), 'buffer_gather')
+        ops.buffer_gather(self.storage_mat, ns, idx_dev, s, r, s1, dv, d, term, None, None)
         return s, r, s1, dv, d, term
 
     def sample(self, idxes=None, out=None):
@@ -121,8 +121,7 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         dev = self.storage_mat.device
         idx = torch.as_tensor(np.asarray(idx, dtype=np.int64)).to(dev)
         val = torch.as_tensor(np.asarray(val, dtype=np.float64)).to(dev)
-        check(lib.cacto_segtree_update(ptr(self._it_sum._value), ptr(self._it_min._value), self._capacity, ptr(idx), ptr(val),
-                                       idx.numel(), ptr(self._stamp), stream_ptr()), 'segtree_update')
+        ops.segtree_update(self._it_sum._value, self._it_min._value, self._capacity, idx, val, self._stamp)
 
     def _on_add(self, n):
         """replay_buffer.py:133-135: new rows enter with max_priority ** alpha in both trees."""
@@ -141,8 +140,7 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         u = torch.as_tensor(np.asarray(uniforms, dtype=np.float64)).to(dev)
         idx = torch.empty(B, dtype=torch.int64, device=dev)
         leaf = torch.empty(B, dtype=torch.float64, device=dev)
-        check(lib.cacto_segtree_sample(ptr(self._it_sum._value), ptr(self._it_min._value), self._capacity, self._max_idx(), ptr(u), B,
-                                       ptr(idx), ptr(leaf), ptr(self._totals), stream_ptr()), 'segtree_sample')
+        ops.segtree_sample(self._it_sum._value, self._it_min._value, self._capacity, self._max_idx(), u, idx, leaf, self._totals)
         return idx, leaf
 
     def sample(self, uniforms=None, out=None):

@@ -6,7 +6,7 @@
 import numpy as np
 import torch
 
-from ._lib import check, lib, ptr, stream_ptr
+from .ops import ops
 from .segment_tree import _dev
 
 
@@ -44,7 +44,6 @@ def rtg_batch(conf, states_list, step_cost_list, lengths=None):
     out = dict(partial=torch.empty(total_knots, **f64), total=torch.empty(total_knots, **f64),
                state_next=torch.empty((total_knots, ns), **f64), done=torch.empty(total_knots, **f64),
                term=torch.empty(total_knots, **f64), ep_return=torch.empty(E, **f64), rwrd=rwrd, states=states, offsets=offsets)
-    check(lib.cacto_rtg_window(ptr(off_dev), E, ptr(rwrd), ptr(states), ns, int(getattr(conf, 'nsteps_TD_N', 0)), int(bool(conf.MC)),
-                               ptr(out['partial']), ptr(out['total']), ptr(out['state_next']), ptr(out['done']), ptr(out['term']),
-                               ptr(out['ep_return']), stream_ptr()), 'rtg_window')
+    ops.rtg_window(off_dev, rwrd, states, ns, int(getattr(conf, 'nsteps_TD_N', 0)), int(bool(conf.MC)), out['partial'], out['total'], out['state_next'],
+                   out['done'], out['term'], out['ep_return'])
     return out

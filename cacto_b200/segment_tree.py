@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from ._lib import check, lib, ptr, stream_ptr
+from .ops import ops
 
 
 def _dev():
@@ -40,9 +41,7 @@ class SegmentTree(object):
         """tree[idx[i]] = val[i] for all i, in order (the last duplicate wins)."""
         idx = torch.as_tensor(np.asarray(idx, dtype=np.int64) if not isinstance(idx, torch.Tensor) else idx).to(_dev(), torch.int64).contiguous()
         val = torch.as_tensor(np.asarray(val, dtype=np.float64) if not isinstance(val, torch.Tensor) else val).to(_dev(), torch.float64).contiguous()
-        s, m = self._ptrs()
-        check(lib.cacto_segtree_update(s, m, self._capacity, ptr(idx), ptr(val), idx.numel(), ptr(self._stamp), stream_ptr()),
-              'segtree_update')
+        ops.segtree_update(self._value if self._kind == 'sum' else None, self._value if self._kind == 'min' else None, self._capacity, idx, val, self._stamp)
 
     def reduce(self, start=0, end=None):
         """segment_tree.py:51-74."""
