@@ -160,8 +160,8 @@ def test_tc_engine_overflow_falls_back_to_fma():
     change the outcome: the reference aborts on NaN only (RL.py:229-231).  Flagged rollouts are re-run on 'fma'."""
     conf, env, rl = setup('manipulator')
     w = rl.actor_model.get_weights()
-    w[0] = w[0] * 1e3                       # first-layer pre-activations ~1e3 x larger: h1 overflows the fp16 high part
-    w[2] = w[2] * 1e-3                      # keep the actions (and the dynamics) in range
+    w[0] = w[0] * 3e4                       # first-layer activations ~1e4: beyond the +-2047 the fp16 high part of 32 h1 can hold
+    w[2] = w[2] / 3e4                       # keep the actions (and the dynamics) in range
     rl.actor_model.set_weights(w)
     X0 = ics(conf, 300, 11)
     X0[:, -1] = (conf.NSTEPS - 20) * conf.dt
