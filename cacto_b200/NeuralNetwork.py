@@ -92,19 +92,40 @@ class Network:
             return
         ops.transpose_params(self.params, self.params_T, self.is_critic, self.ns, self.na)
 
+    def _keras_layer_names(self):
+        """Layer names of the reference's Keras models with weights, in topological order (as in its archived .h5 files)."""
+        L = len(self.dims) - 1
+        if self.kind == 'actor':
+            return ['dense' if l == 0 else f'dense_{l}' for l in range(L)]
+        if self.kind == 'critic_sine':
+            return ['sinusodial_representation_dense' if l == 0 else f'sinusodial_representation_dense_{l}' for l in range(L - 1)] + ['dense_3']
+        return [f'dense_{l}' for l in range(L)]
+
     def save_weights(self, path):
-        """Checkpoint as .npz (the reference writes Keras .h5, RL.py:191-195; .h5 export is listed as next work)."""
-        np.savez(path if str(path).endswith('.npz') else str(path) + '.npz', *self.get_weights())
+        """``<path>.h5``: a Keras-2.11 ``save_weights`` HDF5 file as the reference writes it (RL.py:191-195; h5weights.save_keras_weights);
+        any other path: ``.npz``."""
+        path = str(path)
+        if path.endswith('.h5'):
+            from .h5weights import save_keras_weights
+            save_keras_weights(path, self.get_weights(), self._keras_layer_names())
+            return
+        np.savez(path if path.endswith('.npz') else path + '.npz', *self.get_weights())
 
     def load_weights(self, path):
-        """``.npz`` written by save_weights, or a Keras ``.h5`` file written by the reference (RL.py:91-97,191-195)."""
+        """A Keras ``.h5`` file written by the reference or by save_weights (RL.py:91-97,191-195), or an ``.npz``."""
         import os
         path = str(path)
         if path.endswith('.h5') and not os.path.exists(path) and os.path.exists(path[:-3] + '.npz'):
             path = path[:-3] + '.npz'
         if path.endswith('.h5'):
-            from .h5weights import load_keras_weights
-            self.set_weights(load_keras_weights(path, self.ns))
+            from .h5weights import load_keras_weights, load_keras_weights_by_tree
+            try:
+                w = load_keras_weights_by_tree(path)         # Keras' own rule: the order of the layer_names attribute
+                if len(w) != len(self._views):
+                    raise ValueError
+            except Exception:
+                w = load_keras_weights(path, self.ns)        # layout-agnostic reader: chains the layers by shape
+            self.set_weights(w)
             return
         z = np.load(path if path.endswith('.npz') else path + '.npz')
         self.set_weights([z[f'arr_{i}'] for i in range(len(self._views))])

@@ -204,13 +204,13 @@ class RL_AC:
         return update_step_counter
 
     def RL_save_weights(self, update_step_counter='final'):
-        """RL.py:191-195 (npz instead of Keras .h5)."""
+        """RL.py:191-195: <NNs_path>/N_try_<n>/{actor,critic,target_critic}_<step>.h5 (Keras save_weights files)."""
         import os
         d = self.conf.NNs_path + "/N_try_{}".format(self.N_try)
         os.makedirs(d, exist_ok=True)
-        self.actor_model.save_weights(d + "/actor_{}".format(update_step_counter))
-        self.critic_model.save_weights(d + "/critic_{}".format(update_step_counter))
-        self.target_critic.save_weights(d + "/target_critic_{}".format(update_step_counter))
+        self.actor_model.save_weights(d + "/actor_{}.h5".format(update_step_counter))
+        self.critic_model.save_weights(d + "/critic_{}.h5".format(update_step_counter))
+        self.target_critic.save_weights(d + "/target_critic_{}.h5".format(update_step_counter))
 
     # ------------------------------------------------------------------------------ reward-to-go
     def rtg_batch(self, TO_states_list, TO_step_cost_list, lengths=None):

@@ -243,3 +243,35 @@ def test_reference_h5_weights_forward():
     v_ref = onn.critic_forward(onn.to_torch([g[f'critic_{i}'] for i in range(10)]), st, conf).numpy()
     assert rel(nn.eval(rl.actor_model, s), a_ref) < 2e-5
     assert rel(nn.eval(rl.critic_model, s), v_ref) < 2e-5
+
+
+def test_save_weights_h5_and_recover_training(tmp_path):
+    """RL_save_weights writes the reference's archive layout (RL.py:191-195) and setup_model(recover_training) reads it back
+    (RL.py:91-97): <path>/N_try_<n>/{actor,critic,target_critic}_<step>.h5."""
+    conf, env, nn, rl, batch = make('manipulator', 64)
+    s, pr, sn, dv, d, term, w = batch
+    rl.update(s, sn, pr, dv, d, term, w, fuse_target=True)             # target != critic
+    conf.NNs_path = str(tmp_path)
+    rl.N_try = 3
+    rl.RL_save_weights(500)
+    import os
+    assert sorted(os.listdir(tmp_path / 'N_try_3')) == ['actor_500.h5', 'critic_500.h5', 'target_critic_500.h5']
+    conf2, env2, nn2, rl2, _ = make('manipulator', 64, seed=9)
+    rl2.setup_model(recover_training=(str(tmp_path), 3, 500))
+    for a, b in ((rl.actor_model, rl2.actor_model), (rl.critic_model, rl2.critic_model), (rl.target_critic, rl2.target_critic)):
+        assert torch.equal(a.params, b.params) and torch.equal(a.params_T, b.params_T)
+
+
+def test_recover_training_from_a_reference_results_directory():
+    """The reference's own archive (Results Single Integrator/Results set test/NNs/N_try_0/*_0.h5) through setup_model."""
+    import os
+    root = '/root/reference/Results Single Integrator/Results set test/NNs'
+    if not os.path.isdir(root):
+        pytest.skip('reference checkout not present')
+    g = golden('h5_si_try0.npz')
+    conf, env, nn, rl, batch = make('single_integrator', 16)
+    rl.setup_model(recover_training=(root, 0, 0))
+    for i, a in enumerate(rl.actor_model.get_weights()):
+        np.testing.assert_array_equal(a, g[f'actor_{i}'])
+    for i, a in enumerate(rl.target_critic.get_weights()):
+        np.testing.assert_array_equal(a, g[f'target_critic_{i}'])

@@ -39,3 +39,50 @@ def test_chain_layers_disambiguates_equal_sizes():
         np.testing.assert_array_equal(out[2 * l + 1], b)
     with pytest.raises(ValueError):
         chain_layers(shuffled, 7)
+
+
+def test_writer_round_trip_and_structure(tmp_path):
+    """save_keras_weights -> a classic HDF5 file with the tree of the reference's own files; read back by the structural reader
+    (which walks superblock / object headers / B-tree / symbol nodes / heaps like libhdf5) and by the layout-agnostic reader."""
+    from cacto_b200.h5weights import load_keras_weights_by_tree, read_tree, save_keras_weights
+    rng = np.random.default_rng(0)
+    dims = [13, 64, 64, 128, 128, 1]
+    w = []
+    for i, o in zip(dims[:-1], dims[1:]):
+        w += [rng.normal(size=(i, o)).astype(np.float32), rng.normal(size=o).astype(np.float32)]
+    names = ['sinusodial_representation_dense', 'sinusodial_representation_dense_1', 'sinusodial_representation_dense_2',
+             'sinusodial_representation_dense_3', 'dense_3']
+    path = str(tmp_path / 'critic_5.h5')
+    save_keras_weights(path, w, names)
+    t = read_tree(path)
+    assert t['attrs']['/'] == {'layer_names': names, 'backend': 'tensorflow', 'keras_version': '2.11.0'}
+    assert t['attrs']['/dense_3']['weight_names'] == ['dense_3/kernel:0', 'dense_3/bias:0']
+    assert t['datasets']['/dense_3/dense_3/kernel:0'].shape == (128, 1)
+    for a, b in zip(load_keras_weights_by_tree(path), w):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(load_keras_weights(path, 13), w):
+        np.testing.assert_array_equal(a, b)
+    blob = open(path, 'rb').read()
+    assert blob[:8] == b'\x89HDF\r\n\x1a\n' and int.from_bytes(blob[40:48], 'little') == len(blob)          # end-of-file address
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout not present')
+def test_structural_reader_walks_the_reference_files_and_rewrite_is_equivalent(tmp_path):
+    """The reference's archived files parse with the same reader, in Keras' layer order; re-written by save_keras_weights they give
+    the same arrays and the same (weight-bearing) layer names."""
+    from cacto_b200.h5weights import load_keras_weights_by_tree, read_tree, save_keras_weights
+    for net, fan_in in (('actor', 3), ('critic', 3), ('target_critic', 3)):
+        src = os.path.join(REF, f'{net}_0.h5')
+        t = read_tree(src)
+        assert t['attrs']['/']['backend'] == 'tensorflow' and t['attrs']['/']['keras_version'] == '2.11.0'
+        by_tree, by_shape = load_keras_weights_by_tree(src), load_keras_weights(src, fan_in)
+        for a, b in zip(by_tree, by_shape):
+            np.testing.assert_array_equal(a, b)
+        names = [n for n in t['attrs']['/']['layer_names'] if t['attrs'].get('/' + n, {}).get('weight_names')]
+        dst = str(tmp_path / f'{net}_0.h5')
+        save_keras_weights(dst, by_tree, names)
+        t2 = read_tree(dst)
+        assert t2['attrs']['/']['layer_names'] == names
+        assert sorted(t2['datasets']) == sorted(t['datasets'])
+        for k in t['datasets']:
+            np.testing.assert_array_equal(t2['datasets'][k], t['datasets'][k])
