@@ -140,6 +140,7 @@ _SIGNATURES = {
     'cacto_segtree_sample': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     'cacto_segtree_find': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    'cacto_host_pow': (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int64]),
     'cacto_buffer_gather': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p]),
     'cacto_peak_fma_fp32': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'cacto_rtg_window': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] +

@@ -10,7 +10,9 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libcacto_b200.so')
 OUT_TORCH = os.path.join(HERE, 'libcacto_b200_torch.so')
-CXX = os.environ.get('CXX', 'g++')
+# the system g++ on purpose (not $CXX): the image's /opt/gcc toolchain links parts of its own libstdc++ statically into a shared
+# object, and iostream code of that copy crashes inside a process that already runs the system libstdc++ (torch)
+CXX = os.environ.get('CACTO_B200_CXX', '/usr/bin/g++')
 BUILD = os.path.join(ROOT, 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']

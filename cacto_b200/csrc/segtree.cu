@@ -29,20 +29,45 @@ __global__ void __launch_bounds__(ST_THREADS) k_segtree_update(double* __restric
   }
   __syncthreads();
   // levels whose node count exceeds one warp: recompute every touched ancestor from its (final) children
+  // (a level is a chain of L2 round trips: 4 nodes per thread are in flight together -- at B = 4096 each of the 1024 threads
+  //  owns exactly 4 leaves -- instead of one after the other; the leaf indices are read once)
   int shift = 1;
-  for (; (cap >> shift) > 32; ++shift) {
-    for (int i = tid; i < n; i += ST_THREADS) {
-      const int node = (cap + (int)idx[i]) >> shift;
-      if (sum) {
-        const double l = sum[2 * node], r = sum[2 * node + 1];
-        sum[node] = __dadd_rn(l, r);
+  if (n <= 4 * ST_THREADS) {                          // every thread walks the level loop (it holds barriers), with 0 - 4 live leaves
+    int leaf[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) leaf[u] = (tid + u * ST_THREADS < n) ? cap + (int)idx[tid + u * ST_THREADS] : -1;
+    for (; (cap >> shift) > 32; ++shift) {
+      double l[4], r[4], a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int node = leaf[u] >> shift;
+        if (leaf[u] >= 0 && sum) { l[u] = sum[2 * node]; r[u] = sum[2 * node + 1]; }
+        if (leaf[u] >= 0 && mn) { a[u] = mn[2 * node]; b[u] = mn[2 * node + 1]; }
       }
-      if (mn) {
-        const double a = mn[2 * node], b = mn[2 * node + 1];
-        mn[node] = (b < a) ? b : a;    // Python min(a, b): b only if strictly smaller
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int node = leaf[u] >> shift;
+        if (leaf[u] >= 0 && sum) sum[node] = __dadd_rn(l[u], r[u]);
+        if (leaf[u] >= 0 && mn) mn[node] = (b[u] < a[u]) ? b[u] : a[u];    // Python min(a, b): b only if strictly smaller
       }
+      __syncthreads();
     }
-    __syncthreads();
+  }
+  if (n > 4 * ST_THREADS) {
+    for (; (cap >> shift) > 32; ++shift) {
+      for (int i = tid; i < n; i += ST_THREADS) {
+        const int node = (cap + (int)idx[i]) >> shift;
+        if (sum) {
+          const double l = sum[2 * node], r = sum[2 * node + 1];
+          sum[node] = __dadd_rn(l, r);
+        }
+        if (mn) {
+          const double a = mn[2 * node], b = mn[2 * node + 1];
+          mn[node] = (b < a) ? b : a;
+        }
+      }
+      __syncthreads();
+    }
   }
   // remaining levels: W = cap >> shift (<= 32) nodes [W, 2W) and everything above, by warp 0
   if (tid < 32) {

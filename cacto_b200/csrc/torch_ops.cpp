@@ -45,35 +45,41 @@ void ok(int rc, const char* what) {
 
 // ---- environment (K1', K2, reward, EE)
 void dyn_step(const Tensor& p, int64_t layout, const Tensor& state, const Tensor& action, Tensor out) {
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
   const int64_t B = layout ? state.size(1) : state.size(0);
-  ok(cacto_dyn_step(sys(p), dtype_code(state), (int)layout, dev(state, "state"), dev(action, state.scalar_type(), "action"), dev(out, state.scalar_type(), "out"), B,
+  ok(cacto_dyn_step(P_, dtype_code(state), (int)layout, dev(state, "state"), dev(action, state.scalar_type(), "action"), dev(out, state.scalar_type(), "out"), B,
                     stream()), "dyn_step");
 }
 void dyn_derivative(const Tensor& p, int64_t layout, const Tensor& state, const Tensor& action, Tensor Fu) {
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
   const int64_t B = layout ? state.size(1) : state.size(0);
-  ok(cacto_dyn_derivative(sys(p), dtype_code(state), (int)layout, dev(state, "state"), dev(action, state.scalar_type(), "action"), dev(Fu, state.scalar_type(), "Fu"), B,
+  ok(cacto_dyn_derivative(P_, dtype_code(state), (int)layout, dev(state, "state"), dev(action, state.scalar_type(), "action"), dev(Fu, state.scalar_type(), "Fu"), B,
                           stream()), "dyn_derivative");
 }
 void dyn_augmented(const Tensor& p, int64_t layout, const Tensor& state, const Tensor& action, Tensor Fx, Tensor Fu) {
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
   const int64_t B = layout ? state.size(1) : state.size(0);
-  ok(cacto_dyn_augmented(sys(p), dtype_code(state), (int)layout, dev(state, "state"), dev(action, state.scalar_type(), "action"), dev(Fx, state.scalar_type(), "Fx"),
+  ok(cacto_dyn_augmented(P_, dtype_code(state), (int)layout, dev(state, "state"), dev(action, state.scalar_type(), "action"), dev(Fx, state.scalar_type(), "Fx"),
                          dev(Fu, state.scalar_type(), "Fu"), B, stream()), "dyn_augmented");
 }
 void ee_position(const Tensor& p, int64_t layout, const Tensor& state, Tensor ee) {
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
   const int64_t B = layout ? state.size(1) : state.size(0);
-  ok(cacto_ee_position(sys(p), dtype_code(state), (int)layout, dev(state, "state"), dev(ee, state.scalar_type(), "ee"), B, stream()), "ee_position");
+  ok(cacto_ee_position(P_, dtype_code(state), (int)layout, dev(state, "state"), dev(ee, state.scalar_type(), "ee"), B, stream()), "ee_position");
 }
 void reward(const Tensor& p, int64_t layout, const Tensor& weights, const Tensor& state, const optional<Tensor>& action, int64_t ur5_plain_ucost, Tensor r,
             const optional<Tensor>& dr_da) {
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
   const int64_t B = layout ? state.size(1) : state.size(0);
-  ok(cacto_reward(sys(p), dtype_code(state), (int)layout, (const double*)dev(weights, F64, "weights"), dev(state, "state"), opt(action, state.scalar_type(), "action"),
+  ok(cacto_reward(P_, dtype_code(state), (int)layout, (const double*)dev(weights, F64, "weights"), dev(state, "state"), opt(action, state.scalar_type(), "action"),
                   (int)ur5_plain_ucost, dev(r, state.scalar_type(), "reward"), opt(dr_da, state.scalar_type(), "dr_da"), B, stream()), "reward");
 }
 
 // ---- rollouts (K1)
 void rollout(const Tensor& p, const optional<Tensor>& actor, int64_t use_actor, const Tensor& ics, const Tensor& horizon, int64_t T_max, Tensor states, Tensor controls,
              Tensor flags, const optional<Tensor>& rewards) {
-  ok(cacto_rollout(sys(p), (const float*)opt(actor, F32, "actor"), (int)use_actor, (const double*)dev(ics, F64, "ics"), (const int32_t*)dev(horizon, at::kInt, "horizon"),
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
+  ok(cacto_rollout(P_, (const float*)opt(actor, F32, "actor"), (int)use_actor, (const double*)dev(ics, F64, "ics"), (const int32_t*)dev(horizon, at::kInt, "horizon"),
                    (int32_t)T_max, (double*)dev(states, F64, "states"), (double*)dev(controls, F64, "controls"), (int32_t*)dev(flags, at::kInt, "flags"),
                    (double*)opt(rewards, F64, "rewards"), ics.size(0), stream()), "rollout");
 }
@@ -82,24 +88,28 @@ void actor_tc16_prepare(const Tensor& actor, int64_t ns, int64_t na, Tensor w2im
 }
 void rollout_tc16(const Tensor& p, const Tensor& actor, const Tensor& w2img, const Tensor& ics, const Tensor& horizon, int64_t T_max, Tensor states, Tensor controls,
                   Tensor flags, const optional<Tensor>& rewards) {
-  ok(cacto_rollout_tc16(sys(p), (const float*)dev(actor, F32, "actor"), dev(w2img, at::kByte, "w2img"), (const double*)dev(ics, F64, "ics"),
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
+  ok(cacto_rollout_tc16(P_, (const float*)dev(actor, F32, "actor"), dev(w2img, at::kByte, "w2img"), (const double*)dev(ics, F64, "ics"),
                         (const int32_t*)dev(horizon, at::kInt, "horizon"), (int32_t)T_max, (double*)dev(states, F64, "states"), (double*)dev(controls, F64, "controls"),
                         (int32_t*)dev(flags, at::kInt, "flags"), (double*)opt(rewards, F64, "rewards"), ics.size(0), stream()), "rollout_tc16");
 }
 
 // ---- networks (N4, N6-N9)
 void actor_forward(const Tensor& p, const Tensor& actor, const Tensor& state, Tensor out) {
-  ok(cacto_actor_forward(sys(p), (const float*)dev(actor, F32, "actor"), (const float*)dev(state, F32, "state"), (float*)dev(out, F32, "out"), state.size(0), stream()),
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
+  ok(cacto_actor_forward(P_, (const float*)dev(actor, F32, "actor"), (const float*)dev(state, F32, "state"), (float*)dev(out, F32, "out"), state.size(0), stream()),
      "actor_forward");
 }
 void critic_forward(const Tensor& p, const Tensor& critic, const Tensor& state, Tensor value, const optional<Tensor>& dV_ds) {
-  ok(cacto_critic_forward(sys(p), (const float*)dev(critic, F32, "critic"), (const float*)dev(state, F32, "state"), (float*)dev(value, F32, "value"),
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
+  ok(cacto_critic_forward(P_, (const float*)dev(critic, F32, "critic"), (const float*)dev(state, F32, "state"), (float*)dev(value, F32, "value"),
                           (float*)opt(dV_ds, F32, "dV_ds"), state.size(0), stream()), "critic_forward");
 }
 void critic_grad(const Tensor& p, const Tensor& critic, const Tensor& critic_T, const Tensor& target, double w_S, int64_t mc, const Tensor& state,
                  const optional<Tensor>& state_next, const Tensor& prtg, const optional<Tensor>& dVdx, const optional<Tensor>& done, const Tensor& weights, double inv_B,
                  Tensor grad, Tensor rtg, Tensor V, Tensor Vt, const optional<Tensor>& loss) {
-  ok(cacto_critic_grad(sys(p), (const float*)dev(critic, F32, "critic"), (const float*)dev(critic_T, F32, "critic_T"), (const float*)dev(target, F32, "target"), (float)w_S,
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
+  ok(cacto_critic_grad(P_, (const float*)dev(critic, F32, "critic"), (const float*)dev(critic_T, F32, "critic_T"), (const float*)dev(target, F32, "target"), (float)w_S,
                        (int)mc, (const float*)dev(state, F32, "state"), (const float*)opt(state_next, F32, "state_next"), (const float*)dev(prtg, F32, "partial_rtg"),
                        (const float*)opt(dVdx, F32, "dVdx"), (const float*)opt(done, F32, "done"), (const float*)dev(weights, F32, "weights"), (float)inv_B,
                        (float*)dev(grad, F32, "grad"), (float*)dev(rtg, F32, "rtg"), (float*)dev(V, F32, "V"), (float*)dev(Vt, F32, "V_target"), (float*)opt(loss, F32, "loss"),
@@ -107,7 +117,8 @@ void critic_grad(const Tensor& p, const Tensor& critic, const Tensor& critic_T, 
 }
 void actor_grad(const Tensor& p, const Tensor& actor, const Tensor& actor_T, const Tensor& critic, const Tensor& critic_T, const Tensor& state, const Tensor& term,
                 double inv_B, Tensor grad, const optional<Tensor>& actions) {
-  ok(cacto_actor_grad(sys(p), (const float*)dev(actor, F32, "actor"), (const float*)dev(actor_T, F32, "actor_T"), (const float*)dev(critic, F32, "critic"),
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
+  ok(cacto_actor_grad(P_, (const float*)dev(actor, F32, "actor"), (const float*)dev(actor_T, F32, "actor_T"), (const float*)dev(critic, F32, "critic"),
                       (const float*)dev(critic_T, F32, "critic_T"), (const float*)dev(state, F32, "state"), (const double*)dev(term, F64, "term"), (float)inv_B,
                       (float*)dev(grad, F32, "grad"), (float*)opt(actions, F32, "actions"), state.size(0), stream()), "actor_grad");
 }
@@ -115,7 +126,8 @@ int64_t update_tc_workspace_bytes(int64_t B, int64_t ns, int64_t na) { return ca
 void critic_grad_tc(const Tensor& p, const Tensor& critic, const Tensor& target, double w_S, int64_t mc, const Tensor& state, const optional<Tensor>& state_next,
                     const Tensor& prtg, const optional<Tensor>& dVdx, const optional<Tensor>& done, const Tensor& weights, double inv_B, Tensor grad, Tensor rtg, Tensor V,
                     Tensor Vt, const optional<Tensor>& loss, Tensor workspace) {
-  ok(cacto_critic_grad_tc(sys(p), (const float*)dev(critic, F32, "critic"), (const float*)dev(target, F32, "target"), (float)w_S, (int)mc,
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
+  ok(cacto_critic_grad_tc(P_, (const float*)dev(critic, F32, "critic"), (const float*)dev(target, F32, "target"), (float)w_S, (int)mc,
                           (const float*)dev(state, F32, "state"), (const float*)opt(state_next, F32, "state_next"), (const float*)dev(prtg, F32, "partial_rtg"),
                           (const float*)opt(dVdx, F32, "dVdx"), (const float*)opt(done, F32, "done"), (const float*)dev(weights, F32, "weights"), (float)inv_B,
                           (float*)dev(grad, F32, "grad"), (float*)dev(rtg, F32, "rtg"), (float*)dev(V, F32, "V"), (float*)dev(Vt, F32, "V_target"),
@@ -123,7 +135,8 @@ void critic_grad_tc(const Tensor& p, const Tensor& critic, const Tensor& target,
 }
 void actor_grad_tc(const Tensor& p, const Tensor& actor, const Tensor& critic, const Tensor& state, const Tensor& term, double inv_B, Tensor grad,
                    const optional<Tensor>& actions, Tensor workspace) {
-  ok(cacto_actor_grad_tc(sys(p), (const float*)dev(actor, F32, "actor"), (const float*)dev(critic, F32, "critic"), (const float*)dev(state, F32, "state"),
+  const cacto_sys_params* P_ = sys(p);      // checked before anything else is touched
+  ok(cacto_actor_grad_tc(P_, (const float*)dev(actor, F32, "actor"), (const float*)dev(critic, F32, "critic"), (const float*)dev(state, F32, "state"),
                          (const double*)dev(term, F64, "term"), (float)inv_B, (float*)dev(grad, F32, "grad"), (float*)opt(actions, F32, "actions"), state.size(0),
                          dev(workspace, at::kByte, "workspace"), workspace.numel(), stream()), "actor_grad_tc");
 }

@@ -119,8 +119,8 @@ class PrioritizedReplayBuffer(ReplayBuffer):
 
     def _tree_update(self, idx, val):
         dev = self.storage_mat.device
-        idx = torch.as_tensor(np.asarray(idx, dtype=np.int64)).to(dev)
-        val = torch.as_tensor(np.asarray(val, dtype=np.float64)).to(dev)
+        idx = idx if isinstance(idx, torch.Tensor) else torch.as_tensor(np.asarray(idx, dtype=np.int64)).to(dev, non_blocking=True)
+        val = torch.as_tensor(np.asarray(val, dtype=np.float64)).to(dev, non_blocking=True)
         ops.segtree_update(self._it_sum._value, self._it_min._value, self._capacity, idx, val, self._stamp)
 
     def _on_add(self, n):
@@ -131,34 +131,44 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         self._tree_update(idx, np.full(n, v, dtype=np.float64))
 
     def _sample_proportional(self, uniforms=None):
-        """replay_buffer.py:139-157.  Returns device idx, device leaf values, host totals
-        (sum(0, max_idx-1), sum(), min())."""
+        """replay_buffer.py:139-157.  Returns device idx, device leaf values; both and the totals (sum(0, max_idx-1), sum(), min())
+        live in ONE packed device block so that sample() brings them to the host with a single copy."""
         B = self.conf.BATCH_SIZE
         if uniforms is None:
             uniforms = np.array([random.random() for _ in range(B)])
         dev = self.storage_mat.device
-        u = torch.as_tensor(np.asarray(uniforms, dtype=np.float64)).to(dev)
-        idx = torch.empty(B, dtype=torch.int64, device=dev)
-        leaf = torch.empty(B, dtype=torch.float64, device=dev)
-        ops.segtree_sample(self._it_sum._value, self._it_min._value, self._capacity, self._max_idx(), u, idx, leaf, self._totals)
+        u = torch.as_tensor(np.asarray(uniforms, dtype=np.float64)).to(dev, non_blocking=True)
+        pk = getattr(self, '_pack', None)
+        if pk is None or pk[0].numel() != 2 * B + 4:
+            pk = (torch.empty(2 * B + 4, dtype=torch.float64, device=dev), torch.empty(2 * B + 4, dtype=torch.float64).pin_memory())
+            self._pack = pk
+        pack = pk[0]
+        idx, leaf, totals = pack[:B].view(torch.int64), pack[B:2 * B], pack[2 * B:2 * B + 3]
+        ops.segtree_sample(self._it_sum._value, self._it_min._value, self._capacity, self._max_idx(), u, idx, leaf, totals)
         return idx, leaf
 
     def sample(self, uniforms=None, out=None):
         """replay_buffer.py:159-188."""
         max_idx = self._max_idx()
         beta = self.conf.prioritized_replay_beta
+        B = self.conf.BATCH_SIZE
         idx_dev, leaf_dev = self._sample_proportional(uniforms)
         s, r, s1, dv, d, term = self._gather(idx_dev, out)
-        # one small D2H: B indices + B leaves + 3 totals; the pow() below must be the host's (bit-exactness)
-        batch_idxes = idx_dev.cpu().numpy().astype(int)
-        leaf = leaf_dev.cpu().numpy()
-        _, tot, mn = self._totals.cpu().numpy()
+        # ONE small D2H (B indices + B leaves + 3 totals, packed); the pow() below must be the host's (bit-exactness)
+        dev_pack, host_pack = self._pack
+        host_pack.copy_(dev_pack, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hp = host_pack.numpy()
+        batch_idxes = hp[:B].view(np.int64).astype(int)
+        leaf = hp[B:2 * B].copy()
+        _, tot, mn = hp[2 * B:2 * B + 3]
+        self._last_idx = (batch_idxes, idx_dev.clone())        # update_priorities of the same batch re-uses the device copy
         p_min = mn / tot
         max_weight = (p_min * max_idx) ** (-beta)
         self.exp_counter[batch_idxes] += 1
         self.priorities[batch_idxes] = leaf / tot
         weights = (self.priorities[batch_idxes] * max_idx) ** (-beta) / max_weight
-        weights = torch.as_tensor(weights.astype(np.float32)).to(s.device)
+        weights = torch.as_tensor(weights.astype(np.float32)).to(s.device, non_blocking=True)
         if out is not None:
             out['weights'].copy_(weights.reshape(-1, 1))
             weights = out['weights']
@@ -168,6 +178,7 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         """replay_buffer.py:190-218.  ``RB_type`` 'PER' (default: |rtg - V|) or 'ReLO' (:193-196: MSE(rtg, V) - MSE(rtg, V_target)
         per sample, clipped to [0, max])."""
         c = self.conf
+        idxes_in = idxes
         rtg = torch.as_tensor(reward_to_go_batch).reshape(-1, 1)
         V = torch.as_tensor(critic_value).reshape(-1, 1)
         if self.RB_type == 'ReLO':
@@ -183,6 +194,13 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         new_p = fresh * td + c.prioritized_replay_eps
         assert len(idxes) == len(new_p)
         assert (new_p > 0).all()
-        vals = np.array([p ** c.prioritized_replay_alpha for p in new_p], dtype=np.float64)
-        self._tree_update(idxes, vals)
+        # p ** alpha with the host libm's pow (what the reference's Python float ** evaluates), one C call for the batch
+        new_p = np.ascontiguousarray(new_p, dtype=np.float64)
+        vals = np.empty_like(new_p)
+        check(lib.cacto_host_pow(new_p.ctypes.data, float(c.prioritized_replay_alpha), vals.ctypes.data, new_p.size), 'host_pow')
+        last = getattr(self, '_last_idx', None)
+        if last is not None and last[0] is idxes_in:              # the indices sample() returned: their device copy is still there
+            self._tree_update(last[1], vals)
+        else:
+            self._tree_update(idxes, vals)
         self._max_priority = max(self._max_priority, float(new_p.max()))

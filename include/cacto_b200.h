@@ -298,6 +298,11 @@ int cacto_segtree_sample(const double* sum_tree, const double* min_tree, int32_t
 int cacto_segtree_find(const double* sum_tree, int32_t capacity, const double* prefix, int32_t n, int64_t* idx,
                        void* stream);
 
+/* Host-side helper of PrioritizedReplayBuffer.update_priorities (replay_buffer.py:210-216): out[i] = pow(x[i], exponent) with
+ * the C library's pow -- what CPython's `priority ** alpha` evaluates -- on HOST arrays (the one entry point that takes host
+ * pointers and launches nothing: the bits of p ** alpha must be the host libm's for the trees to stay bit-exact). */
+int cacto_host_pow(const double* x_host, double exponent, double* out_host, int64_t n);
+
 /* ---- R1/R2: gather of sampled rows (replay_buffer.py:47-61,178-188): storage[cap][3ns+3] fp64 ->
  *      float32 blocks; term stays fp64.  exp_counter (fp64[cap]) is incremented once per distinct index
  *      when non-NULL (replay_buffer.py:174). */
