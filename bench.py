@@ -286,6 +286,8 @@ def run_b200(args):
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback on the product path)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    from cacto_b200.parallel import bind_to_gpu_numa_node
+    placement = bind_to_gpu_numa_node(local_rank)          # before any pinned allocation: first touch on the GPU's node
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     from cacto_b200 import _lib, environment as genv
@@ -563,7 +565,8 @@ def run_b200(args):
                                    f'{B} rollouts x {T} steps per GPU (1 M over 8 GPUs), seeded-init actor {ns}->256->256->{na}',
                        'rollouts_per_gpu': B, 'horizon': T, 'engine': args.engine,
                        'l2': 'flushed between timed steps (256 MiB write); outputs 1.06 GB/step',
-                       'parallelism': f'dp{world} over independent rollouts, no collective on the rollout path'},
+                       'parallelism': f'dp{world} over independent rollouts, no collective on the rollout path',
+                       'host_placement_rank0': placement},
             'roofline': roof,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'note': 'RL_AC.rollout_to_host (pipelined): 8 sub-batches, the copy engine moves the fp64 trajectories of sub-batch k into pinned host memory '

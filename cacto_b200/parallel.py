@@ -170,3 +170,42 @@ class PeerReduce:
 
     def table(self, net):
         return self._tables[id(net)]
+
+
+# ------------------------------------------------------------------------------------------ host placement
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (``/sys/bus/pci/devices/<bdf>/numa_node``), so that
+    the pinned host buffers of the warm-start path (RL_AC.rollout_to_host: 1 GB of fp64 trajectories per step and GPU) are
+    first-touched on that node and the feeder threads run next to them.  Without it the 8 ranks of a box all allocate on node 0
+    and share its memory controllers and one socket's PCIe root (round 1: 1.9 x e2e throughput from 1 to 8 GPUs).
+    Returns a dict describing what was done (for the bench line); never raises -- placement is an optimisation."""
+    import os
+    info = {'device': int(device_index), 'numa_node': None, 'cpus': None, 'bound': False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = '%04x:%02x:%02x.0' % (int(getattr(p, 'pci_domain_id', 0)), int(p.pci_bus_id), int(p.pci_device_id))
+        node = int(open(f'/sys/bus/pci/devices/{bdf}/numa_node').read())
+        info['numa_node'] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info['cpus'] = '%d cpus of node %d' % (len(allowed), node)
+            info['bound'] = True
+            try:                                   # prefer the node for future allocations of this process (libnuma, if present)
+                import ctypes
+                numa = ctypes.CDLL('libnuma.so.1')
+                if numa.numa_available() >= 0:
+                    numa.numa_set_preferred(node)
+                    info['preferred'] = True
+            except OSError:
+                pass
+    except Exception as exc:                       # no sysfs entry (container), odd PCI ids: report and go on
+        info['error'] = f'{type(exc).__name__}: {exc}'
+    return info
