@@ -438,8 +438,15 @@ def run_b200(args):
         if tc:
             leg['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': ach / bf16_peak,
                                'ceiling_3xfp16': bf16_peak / 3.0, 'frac_of_3xfp16_ceiling': ach / (bf16_peak / 3.0), 'peak_source': peak_src,
-                               'note': 'layer-wise sweeps over 128-sample tiles; the sweeps are bound by workspace traffic (~10 KB per sample '
-                                       'through L2/HBM) and CUDA-core epilogues, not by the tensor pipe (profiles/README.md)'}
+                               'note': 'layer-wise sweeps over 128-sample tiles: bound by the per-sample intermediates that travel through the '
+                                       'workspace (L2 / HBM) and by CUDA-core epilogues, not by the tensor pipe (profiles/README.md)'}
+            # the implementation's own traffic: floats written + read per sample by the sweeps and the weight-gradient GEMMs
+            # (critic 2468 w + 3642 r, actor 1480 w + 2262 r: DESIGN.md section 4), against the measured HBM copy bandwidth
+            ws_bytes = 4.0 * (2468 + 3642 + 1480 + 2262) * B_local
+            hbm = peaks.get('hbm_gbs') or 6650.0
+            leg['workspace_traffic'] = {'bytes_per_update': ws_bytes, 'achieved_gbs': ws_bytes / (best_us * 1e-6) / 1e9, 'hbm_peak_gbs': hbm,
+                                        'frac_of_hbm': ws_bytes / (best_us * 1e-6) / 1e9 / hbm,
+                                        'note': 'analytic workspace bytes (most of them L2 hits at these sizes: 126 MB L2), not a DRAM counter'}
         else:
             leg['roofline'] = {'bound': 'fp32_fma' if B_local >= 1024 else 'latency', 'achieved': ach, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
                                'frac': ach / fma_peak_tflops, 'peak_source': 'cacto_peak_fma_fp32 measured in this run'}

@@ -96,7 +96,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
 // shared slots and an mbarrier counts the landed bytes; all threads then read the chunk with conflict-free
 // LDS.128.  While a chunk is consumed the next one (of the same GEMM or the first chunk of the next GEMM)
 // is already in flight, so the L2 latency of a weight fetch is paid once per kernel, not once per k-step
-// (the latter made the B = 64 update latency-bound: profiles/r1_update_latency.md).
+// (the latter made the B = 64 update latency-bound: profiles/README.md, "K3 at the reference's batch size").
 constexpr int W_CHUNK = 8192;   // floats per slot (32 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
