@@ -244,6 +244,7 @@ class RL_AC:
     # Rollout engines: 'tc' = tcgen05 fp16-split persistent kernel (cacto_rollout_tc16, default), 'tf32' = tcgen05 3xTF32
     # kernel (cacto_rollout_tc), 'fma' = fp32 CUDA-core kernel (cacto_rollout; also runs the ep = 0 zero-control rollouts).
     rollout_engine = 'tc'
+    ur5_on_tc16 = False
 
     def _launch_rollout(self, ep, ics, hz, T_max, states, controls, flags, rewards, B, engine=None, prepare=True):
         engine = engine or self.rollout_engine
@@ -251,8 +252,13 @@ class RL_AC:
             raise ValueError('unknown rollout engine %r' % (engine,))
         use_actor = int(ep != 0)
         am = self.actor_model
-        if engine in ('tc', 'tc2') and am.ns > 8:
-            engine = 'tf32'        # UR5: 13 inputs exceed the fp16 kernel's shared-memory budget; its dynamics dominate anyway
+        if engine in ('tc', 'tc2') and am.ns > 8 and not self.ur5_on_tc16:
+            # UR5 is bound by its fp64 articulated-body dynamics, not by the actor: the fp16 kernel (which can run it: 4-slot W2 ring,
+            # streamed layer 1) has one dynamics thread per rollout and 256 rollouts per SM and takes 7.04 ms for 32768 x 100 steps
+            # against 5.62 ms of the 3xTF32 kernel (profiles/README.md), so 'tc' means the latter for UR5 unless ur5_on_tc16 is set
+            engine = 'tf32'
+        elif engine == 'tc2' and am.ns > 8:
+            engine = 'tc'
         if use_actor and engine == 'tc':
             img = getattr(self, '_w2img16', None)
             if img is None:
@@ -320,7 +326,7 @@ class RL_AC:
         actors are unbounded.  Flagged rollouts are therefore rolled out again on the fp32 'fma' engine and
         patched into the outputs; only rollouts that fail there too (a NaN state, as in the reference) stay flagged.
         Costs one device->host read of the failure count per call.  Returns the number of rollouts re-run."""
-        if ep == 0 or (engine or self.rollout_engine) not in ('tc', 'tc2') or self.actor_model.ns > 8:
+        if ep == 0 or (engine or self.rollout_engine) not in ('tc', 'tc2') or (self.actor_model.ns > 8 and not self.ur5_on_tc16):
             return 0
         bad = (flags == 0).nonzero().reshape(-1)
         n = int(bad.numel())
@@ -403,7 +409,7 @@ class RL_AC:
             flags_host.copy_(buf[2], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         # fp16-range failures of the 'tc' engines (see _retry_flagged): re-run on 'fma' and patch the host buffers
-        if ep != 0 and (engine or self.rollout_engine) in ('tc', 'tc2') and self.actor_model.ns <= 8:
+        if ep != 0 and (engine or self.rollout_engine) in ('tc', 'tc2') and (self.actor_model.ns <= 8 or self.ur5_on_tc16):
             bad = (flags_host == 0).nonzero().reshape(-1)
             if bad.numel() > 0:
                 r = self.rollout_batch(ics_host[bad], ep, horizon=hz_np[bad.numpy()], engine='fma')

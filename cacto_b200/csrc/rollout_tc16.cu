@@ -54,7 +54,8 @@ constexpr float T16_SA = 32.f;
 
 template <int NS>
 struct Tc16Smem {
-  static constexpr int RING = T16_RING, XW = NS > 8 ? 16 : 8;
+  // UR5 (13 inputs: 13 KB of W1, 16 KB of state exchange) keeps a 4-slot W2 ring so that everything fits in 227 KB
+  static constexpr int RING = NS > 8 ? T16_RING / 2 : T16_RING, XW = NS > 8 ? 16 : 8;
   alignas(1024) unsigned char B[RING][2 * T16_B_IMG];                  // W2 ring: [slot][hi | lo]           144 KB
   alignas(1024) unsigned char A[T16_SLOTS][T16_STAGES][2 * T16_A_IMG]; // A stages: [slot][stage][hi | lo]    48 KB
   alignas(16) float W1[NS][ACTOR_H];                                   // S_a * W1                           7-13 KB
@@ -232,9 +233,10 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
   constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA, NS = NX + 1;
   constexpr int WORKERS = T16_WORKERS, THREADS = T16_THREADS;
   static_assert(NS <= 16, "the layer-1 register tile holds at most 16 inputs");
-  static_assert(T16_NCHUNK % T16_STAGES == 0 && T16_NCHUNK % T16_RING == 0 && T16_HALF % T16_RING == 0, "compile-time stage / ring indices");
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
   using Smem = Tc16Smem<NS>;
+  constexpr int RING = Smem::RING;
+  static_assert(T16_NCHUNK % T16_STAGES == 0 && T16_NCHUNK % RING == 0 && T16_HALF % RING == 0, "compile-time stage / ring indices");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const ActorLayout L(NS, NA);
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // warp: provably warp-uniform
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
   if (tid < 8) sm.b3[tid] = tid < NA ? actor[L.b3 + tid] : 0.f;
   for (int i = tid; i < my_tiles; i += THREADS) sm.tile_tmax[i] = 0;
   if (tid == 0) {
-    for (int s = 0; s < T16_RING / 2; ++s) { t16_mbar_init(&sm.b_full[s], 1); t16_mbar_init(&sm.b_empty[s], 2); }
+    for (int s = 0; s < RING / 2; ++s) { t16_mbar_init(&sm.b_full[s], 1); t16_mbar_init(&sm.b_empty[s], 2); }
     for (int m = 0; m < T16_SLOTS; ++m) {
       for (int s = 0; s < T16_STAGES; ++s) t16_mbar_init(&sm.a_full[m][s], T16_TILE / 2);
       for (int s = 0; s < T16_STAGES / 2; ++s) t16_mbar_init(&sm.a_empty[m][s], 1);
@@ -359,26 +361,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
           const int ci = (g_begin[m] + kc) & (T16_NCHUNK - 1);            // slot 1 visits the chunks in rotated order
           const int st = qc % T16_STAGES;
           const int c = ci * T16_KC + 8 * l1_ku;
-          ulonglong2 wA[NS], wB[NS];
-#pragma unroll
-          for (int j = 0; j < NS; ++j) {
-            wA[j] = *reinterpret_cast<const ulonglong2*>(&sm.W1[j][c]);
-            wB[j] = *reinterpret_cast<const ulonglong2*>(&sm.W1[j][c + 4]);
-          }
           const ulonglong2 bA = *reinterpret_cast<const ulonglong2*>(&sm.b1[c]), bB = *reinterpret_cast<const ulonglong2*>(&sm.b1[c + 4]);
-          WEV(2);                                // chunk: W1 loaded, about to wait for the stage
-          if (qc >= T16_STAGES) t16_mbar_wait(&sm.a_empty[m][st >> 1], (uint32_t)((qc / T16_STAGES - 1) & 1));   // stage pair (st >> 1) of chunk pair qc / 2
-          WEV(3);                                // stage free
           unsigned char* dst = a_dst0 + st * (2 * T16_A_IMG);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint64_t z[4] = {bA.x, bA.y, bB.x, bB.y};
-#pragma unroll
-            for (int j = 0; j < NS; ++j) {
-              const uint64_t xj = pk(xn[i][j], xn[i][j]);
-              z[0] = fma2(xj, wA[j].x, z[0]); z[1] = fma2(xj, wA[j].y, z[1]);
-              z[2] = fma2(xj, wB[j].x, z[2]); z[3] = fma2(xj, wB[j].y, z[3]);
-            }
+          auto finish_row = [&](int i, const uint64_t (&z)[4]) {              // LeakyReLU, hi / lo split, 16-byte stores of row lane + 32 i
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
@@ -392,6 +377,49 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
             }
             *reinterpret_cast<uint4*>(dst + 512 * i) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(dst + 512 * i + T16_A_IMG) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          };
+          if constexpr (NS <= 8) {
+            // all of W1's chunk columns in registers (8 registers per input), rows one after the other
+            ulonglong2 wA[NS], wB[NS];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+              wA[j] = *reinterpret_cast<const ulonglong2*>(&sm.W1[j][c]);
+              wB[j] = *reinterpret_cast<const ulonglong2*>(&sm.W1[j][c + 4]);
+            }
+            WEV(2);                                // chunk: W1 loaded, about to wait for the stage
+            if (qc >= T16_STAGES) t16_mbar_wait(&sm.a_empty[m][st >> 1], (uint32_t)((qc / T16_STAGES - 1) & 1));   // stage pair (st >> 1) of chunk pair qc / 2
+            WEV(3);                                // stage free
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint64_t z[4] = {bA.x, bA.y, bB.x, bB.y};
+#pragma unroll
+              for (int j = 0; j < NS; ++j) {
+                const uint64_t xj = pk(xn[i][j], xn[i][j]);
+                z[0] = fma2(xj, wA[j].x, z[0]); z[1] = fma2(xj, wA[j].y, z[1]);
+                z[2] = fma2(xj, wB[j].x, z[2]); z[3] = fma2(xj, wB[j].y, z[3]);
+              }
+              finish_row(i, z);
+            }
+          } else {
+            // wide inputs (UR5: 13): inputs outermost, the 4 rows' accumulators stay live (32 registers) and W1 streams through
+            uint64_t z[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { z[i][0] = bA.x; z[i][1] = bA.y; z[i][2] = bB.x; z[i][3] = bB.y; }
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+              const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(&sm.W1[j][c]), wb = *reinterpret_cast<const ulonglong2*>(&sm.W1[j][c + 4]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint64_t xj = pk(xn[i][j], xn[i][j]);
+                z[i][0] = fma2(xj, wa.x, z[i][0]); z[i][1] = fma2(xj, wa.y, z[i][1]);
+                z[i][2] = fma2(xj, wb.x, z[i][2]); z[i][3] = fma2(xj, wb.y, z[i][3]);
+              }
+            }
+            WEV(2);
+            if (qc >= T16_STAGES) t16_mbar_wait(&sm.a_empty[m][st >> 1], (uint32_t)((qc / T16_STAGES - 1) & 1));
+            WEV(3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) finish_row(i, z[i]);
           }
 #ifndef T16_EXP_NO_FENCE      // timing experiment only
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the UMMA (async proxy)
@@ -524,14 +552,14 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
     constexpr uint32_t lboA = (T16_TILE / 8) * 128, lboB = (ACTOR_H / 8) * 128;
     const uint32_t d = tmem + (uint32_t)(m * ACTOR_H);
     const uint32_t a_base = smem_u32(&sm.A[m][0][0]), b_base = smem_u32(&sm.B[0][0]);
-    const uint32_t pb0 = (uint32_t)(gb / T16_RING) & 1u;         // ring phase of this slot's first chunk (gb is 0 or T16_HALF = T16_RING)
+    const uint32_t pb0 = (uint32_t)(gb / RING) & 1u;             // ring phase of this slot's first chunk (gb is 0 or T16_HALF, a multiple of RING)
 #ifdef T16_TRACE
     int trace_n = 0;
 #endif
     // K-chunks are issued in pairs (one fence / elect / two commits per 6 UMMAs): the issuer warp shares its scheduler with two
     // busy worker warps and retires an instruction only every ~24 cycles, so its instruction count per chunk IS its chunk time.
     // The barrier polls of pair kp + 1 are issued before the UMMA block of pair kp.
-    constexpr int NPAIR = T16_NCHUNK / 2, RPAIR = T16_RING / 2, SPAIR = T16_STAGES / 2;
+    constexpr int NPAIR = T16_NCHUNK / 2, RPAIR = RING / 2, SPAIR = T16_STAGES / 2;
     bool rdy_b = t16_mbar_try(smem_u32(&sm.b_full[0]), pb0);
     bool rdy_a0 = t16_mbar_try(smem_u32(&sm.a_full[m][0]), 0u), rdy_a1 = t16_mbar_try(smem_u32(&sm.a_full[m][1]), 0u);
     for (int g0 = gb; g0 < ge; g0 += T16_NCHUNK) {                // one step: stages, ring slots and parities are compile-time
@@ -580,7 +608,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
     const int gt = __shfl_sync(0xffffffffu, g_total, 0) / 2;       // chunk pairs (the ranges are multiples of T16_HALF)
     int rp = 0, rphase = 0, kp = 0;
     for (int g = 0; g < gt; ++g) {
-      if (g >= T16_RING / 2) t16_mbar_wait(&sm.b_empty[rp], (uint32_t)(rphase ^ 1));
+      if (g >= RING / 2) t16_mbar_wait(&sm.b_empty[rp], (uint32_t)(rphase ^ 1));
       if (t16_elect_one()) {
         const uint32_t mb = smem_u32(&sm.b_full[rp]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
@@ -589,7 +617,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) k_rollout_tc16(const __grid_co
                      : "memory");
       }
       __syncwarp();
-      if (++rp == T16_RING / 2) { rp = 0; rphase ^= 1; }
+      if (++rp == RING / 2) { rp = 0; rphase ^= 1; }
       if (++kp == T16_NCHUNK / 2) kp = 0;
     }
   }
@@ -661,7 +689,7 @@ extern "C" int cacto_rollout_tc16(const cacto_sys_params* p, const float* actor_
     case CACTO_CAR: return launch_rollout_tc16<CACTO_CAR>(*p, actor_params, img, ics, horizon, T_max, states, controls, flags, rewards, B, st);
     case CACTO_CAR_PARK: return launch_rollout_tc16<CACTO_CAR_PARK>(*p, actor_params, img, ics, horizon, T_max, states, controls, flags, rewards, B, st);
     case CACTO_MANIPULATOR: return launch_rollout_tc16<CACTO_MANIPULATOR>(*p, actor_params, img, ics, horizon, T_max, states, controls, flags, rewards, B, st);
-    case CACTO_UR5: return CACTO_E_SYSTEM;     // 13 inputs do not fit this kernel's shared-memory budget: use cacto_rollout_tc / cacto_rollout
+    case CACTO_UR5: return launch_rollout_tc16<CACTO_UR5>(*p, actor_params, img, ics, horizon, T_max, states, controls, flags, rewards, B, st);
     default: return CACTO_E_SYSTEM;
   }
 }

@@ -133,6 +133,7 @@ int cacto_rollout_tc(const cacto_sys_params* p, const float* actor_params, const
  *      (a = a_hi + a_lo, w = w_hi + w_lo; a w ~= a_hi w_hi + a_hi w_lo + a_lo w_hi, fp32 accumulation in TMEM: the
  *      accuracy class of 3xTF32 at twice the rate) by persistent CTAs that keep two 128-rollout tiles in flight.
  *      Range limit: hidden activations beyond +-2047 overflow the fp16 high part; such a rollout is flagged failed.
+ *      All six systems (UR5 with a 4-slot W2 ring; its fp64 dynamics dominate and cacto_rollout_tc is faster for it).
  *      w2img (cacto_actor_tc16_image_bytes() bytes, 128-byte aligned, caller-owned) is the scaled, split, UMMA-laid-out
  *      image of the actor's W2 built by cacto_actor_tc16_prepare; rebuild it whenever the actor changes. */
 int64_t cacto_actor_tc16_image_bytes(void);

@@ -190,3 +190,25 @@ def test_tc_engine_overflow_falls_back_to_fma():
     hz = ref['horizon'].cpu().numpy()
     for b_ in (0, 150, 299):
         np.testing.assert_allclose(sh[:hz[b_] + 1, :, b_].numpy(), b[:hz[b_] + 1, :, b_], rtol=1e-4, atol=1e-6)
+
+
+def test_ur5_on_the_fp16_engine_matches_oracle():
+    """cacto_rollout_tc16 also runs UR5 (4-slot W2 ring, streamed layer 1); RL_AC keeps the 3xTF32 kernel as UR5's default because
+    it is faster there (the dynamics dominate), so the path is exercised explicitly."""
+    conf, env, rl = setup('ur5')
+    rl.ur5_on_tc16 = True
+    X0 = ics(conf, 200, 5)
+    X0[:, -1] = (conf.NSTEPS - 15) * conf.dt
+    out = rl.rollout_batch(X0, 1, engine='tc')
+    ref = rl.rollout_batch(X0, 1, engine='fma')
+    assert out['success'].cpu().numpy().all()
+    a, b = out['states'].cpu().numpy(), ref['states'].cpu().numpy()
+    m = ~np.isnan(b)
+    assert (np.isnan(a) == np.isnan(b)).all()
+    assert np.abs(a[m] - b[m]).max() <= 1e-5 * np.abs(b[m]).max()
+    oenv = osys.make_env(conf)
+    ap = onn.to_torch(rl.actor_model.get_weights())
+    ev = lambda x: onn.actor_forward(ap, torch.tensor(x, dtype=torch.float32), conf).detach().numpy()[0]
+    S = out['states'].permute(2, 0, 1).cpu().numpy()
+    _, st, ct, T, ok = ortg.create_to_init(conf, oenv, ev, 1, X0[3])
+    assert ok and np.abs(S[3, :T + 1] - st).max() <= 1e-4 * max(1.0, np.abs(st).max())
