@@ -461,18 +461,28 @@ def run_b200(args):
             rows[:, 3 * ns_ + 2] = (rows[:, 3 * ns_ + 2] > 2.3).double()
             buf.add_rows(rows)
             np.random.seed(0)
-            g_ = getattr(r_, 'update_graph', None)
+            ug_ = None
+            if world == 1 or r_._peer is not None:
+                try:
+                    ug_ = r_.make_update_graph(B_local)          # learn_and_update's default: the update replayed as a CUDA graph
+                except Exception:
+                    ug_ = None
             r_.peer_barrier()
             for it in range(3 + e2e_updates):
                 if it == 3:
                     torch.cuda.synchronize()
                     t0_ = time.perf_counter()
-                bs = buf.sample()
-                r_.update(bs[0], bs[2], bs[1], bs[3], bs[4], bs[5], bs[6], fuse_target=True, synced=True)
+                if ug_ is not None:
+                    buf.sample(out=ug_.io)
+                    ug_.replay()
+                else:
+                    bs = buf.sample()
+                    r_.update(bs[0], bs[2], bs[1], bs[3], bs[4], bs[5], bs[6], fuse_target=True, synced=True)
                 loss_host = float(nn_.last_critic_loss)          # device -> host read of the step's result
             e2e_s_ = max_over_ranks(time.perf_counter() - t0_)
             leg['e2e'] = {'value': e2e_updates / e2e_s_, 'unit': 'updates/s', 'h2d_bytes_per_step': 8 * B_local, 'd2h_bytes_per_step': 4,
-                          'note': 'ReplayBuffer.sample (host index draw + device gather) + RL_AC.update (eager launches) + loss read-back per update; '
+                          'note': 'as RL_AC.learn_and_update runs it: ReplayBuffer.sample (host index draw + H2D + device gather into the graph inputs) + '
+                                  'the update replayed as a CUDA graph + loss read-back per update; '
                                   f'last loss {loss_host:.4g}'}
         del r_, nn_
         return leg

@@ -185,8 +185,12 @@ class RL_AC:
 
     def learn_and_update(self, update_step_counter, buffer, ep):
         """RL.py:120-143."""
-        graph = getattr(self, 'update_graph', None)
         self.peer_barrier()                             # data-parallel ranks arrive here with minutes of skew (host TO solves)
+        graph = getattr(self, 'update_graph', None)
+        if graph is None and self.use_update_graph:     # the update as a replayed CUDA graph (built once per batch size): at the
+            graph = self.update_graph = self.make_update_graph(self.conf.BATCH_SIZE)       # conf batches it is launch-latency bound
+        if graph is not None and graph.B != int(self.conf.BATCH_SIZE):
+            graph = self.update_graph = self.make_update_graph(self.conf.BATCH_SIZE)
         for _ in range(int(self.conf.UPDATE_LOOPS[ep])):
             if graph is not None:                       # captured update: the sampled rows land in the graph's input tensors
                 batch_idxes = buffer.sample(out=graph.io)[7]
@@ -245,6 +249,7 @@ class RL_AC:
     # kernel (cacto_rollout_tc), 'fma' = fp32 CUDA-core kernel (cacto_rollout; also runs the ep = 0 zero-control rollouts).
     rollout_engine = 'tc'
     ur5_on_tc16 = False
+    use_update_graph = True          # learn_and_update replays a captured update (RL.UpdateGraph) instead of launching it eagerly
 
     def _launch_rollout(self, ep, ics, hz, T_max, states, controls, flags, rewards, B, engine=None, prepare=True):
         engine = engine or self.rollout_engine

@@ -73,13 +73,15 @@ def test_learn_and_update_runs_with_both_buffers(alpha):
     random.seed(0)
     np.random.seed(0)
     w0 = weights_of(rl)
+    rl.use_update_graph = False                    # eager launches first ...
     cnt = rl.learn_and_update(0, buf, 0)
-    assert cnt == 12 and rl.actor_optimizer.iterations == 12
+    assert cnt == 12 and rl.actor_optimizer.iterations == 12 and getattr(rl, 'update_graph', None) is None
     w1 = weights_of(rl)
     assert all(np.isfinite(w).all() for w in w1)
     assert any(np.abs(a - b).max() > 0 for a, b in zip(w0, w1))
-    rl.update_graph = rl.make_update_graph()
+    rl.use_update_graph = True                     # ... then the default: the graph is built on first use
     cnt = rl.learn_and_update(cnt, buf, 0)
+    assert rl.update_graph.B == conf.BATCH_SIZE
     assert cnt == 24 and rl.critic_optimizer.iterations == 24
     assert all(np.isfinite(w).all() for w in weights_of(rl))
     if alpha:
