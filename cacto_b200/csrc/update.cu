@@ -769,10 +769,20 @@ __device__ __forceinline__ int64_t transposed_index(const LayerTable& T, int64_t
   return i;
 }
 
+// 1 - h for a hyperparameter h that arrived as a float: TF 2.11's optimizer (and RL.py:116-118's Polyak step) form 1 - beta / 1 - tau in
+// Python double precision from the decimal literal and only then round to fp32, which is not 1.f - (float)h (for beta2 = 0.999 the two
+// differ by 1.3e-5 relative).  The float encodes at most 7 significant decimals of the literal: recover them, subtract in double.
+static inline float one_minus(float h) {
+  if (!(h > 0.f && h < 1.f)) return 1.f - h;
+  double scale = 1e7;
+  for (double a = h; a < 0.1; a *= 10.0) scale *= 10.0;      // keep 7 significant digits for small h (tau = 0.001)
+  return (float)(1.0 - nearbyint((double)h * scale) / scale);
+}
+
 // p -= alpha * m / (sqrt(v) + eps) with m += (g - m)(1 - b1), v += (g^2 - v)(1 - b2)   (SURVEY.md A.5), the Polyak target
 // update (RL.py:116-118) and the refresh of the transposed copy, for parameter i with gradient gi
 __device__ __forceinline__ void adam_element(int64_t i, float gi, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float alpha,
-                                             float omb1, float omb2, float eps, float* __restrict__ target, float tau, float* __restrict__ pT,
+                                             float omb1, float omb2, float eps, float* __restrict__ target, float2 tt, float* __restrict__ pT,
                                              const LayerTable& T) {
   float mi = m[i], vi = v[i];
   mi += (gi - mi) * omb1;
@@ -781,13 +791,13 @@ __device__ __forceinline__ void adam_element(int64_t i, float gi, float* __restr
   v[i] = vi;
   const float pi = p[i] - (mi * alpha) / (sqrtf(vi) + eps);
   p[i] = pi;
-  if (target != nullptr) target[i] = pi * tau + target[i] * (1.f - tau);
+  if (target != nullptr) target[i] = pi * tt.x + target[i] * tt.y;
   if (pT != nullptr) pT[transposed_index(T, i)] = pi;
 }
 
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                               float alpha, const float* __restrict__ alpha_dev, float omb1, float omb2, float eps,
-                                              float* __restrict__ target, float tau,
+                                              float* __restrict__ target, float2 tt,
                                               float* __restrict__ pT, LayerTable T, int64_t n) {
   pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,7 +805,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __re
   const float gi = g[i];
   g[i] = 0.f;
   if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);     // device-side schedule (CUDA-graph replays)
-  adam_element(i, gi, p, m, v, alpha, omb1, omb2, eps, target, tau, pT, T);
+  adam_element(i, gi, p, m, v, alpha, omb1, omb2, eps, target, tt, pT, T);
 }
 
 // ---- data-parallel update: the gradient all-reduce fused into the Adam step over NVLink peer memory.
@@ -815,7 +825,7 @@ struct PeerTable {
 
 __global__ void __launch_bounds__(256) k_adam_peer(float* __restrict__ p, PeerTable R, float* __restrict__ zero_other, int64_t n_other,
                                                    float* __restrict__ m, float* __restrict__ v, const float* __restrict__ alpha_dev, float omb1,
-                                                   float omb2, float eps, float* __restrict__ target, float tau, float* __restrict__ pT,
+                                                   float omb2, float eps, float* __restrict__ target, float2 tt, float* __restrict__ pT,
                                                    LayerTable T, int64_t n) {
   pdl_wait();
   // words [0, CACTO_MAX_PEERS) of a rank's flag row: arrival epochs written by the peers; [CACTO_MAX_PEERS]: number of steps this
@@ -857,7 +867,7 @@ __global__ void __launch_bounds__(256) k_adam_peer(float* __restrict__ p, PeerTa
 #pragma unroll
     for (int r = 1; r < CACTO_MAX_PEERS; ++r)              // ... summed in rank order
       if (r < R.world) gi += x[r];
-    adam_element(i, gi, p, m, v, alpha, omb1, omb2, eps, target, tau, pT, T);
+    adam_element(i, gi, p, m, v, alpha, omb1, omb2, eps, target, tt, pT, T);
   }
   __syncthreads();
   if (threadIdx.x == 0) {                                  // the last CTA to finish advances the epoch base for the next launch
@@ -1068,7 +1078,7 @@ extern "C" int cacto_adam_step(float* params, float* grad, float* m, float* v, f
     return CACTO_E_SIZE;
   }
   if (cudaError_t le = launch_pdl(k_adam, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, params, grad, m, v, alpha_t, alpha_dev_or_null,
-                                  1.f - beta1, 1.f - beta2, eps, target_or_null, tau, params_T_or_null, T, n))
+                                  one_minus(beta1), one_minus(beta2), eps, target_or_null, make_float2(tau, one_minus(tau)), params_T_or_null, T, n))
     return (int)le;
   CACTO_LAUNCH_CHECK();
   return 0;
@@ -1101,7 +1111,7 @@ extern "C" int cacto_adam_step_peer(float* params, const float* const* peer_grad
   int64_t ctas = (n + 255) / 256;
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (cudaError_t le = launch_pdl(k_adam_peer, (unsigned)ctas, 256, 0, (cudaStream_t)stream, params, R, zero_other_or_null, n_other, m, v, alpha_dev,
-                                  1.f - beta1, 1.f - beta2, eps, target_or_null, tau, params_T_or_null, T, n))
+                                  one_minus(beta1), one_minus(beta2), eps, target_or_null, make_float2(tau, one_minus(tau)), params_T_or_null, T, n))
     return (int)le;
   CACTO_LAUNCH_CHECK();
   return 0;
