@@ -187,8 +187,11 @@ class RL_AC:
         """RL.py:120-143."""
         self.peer_barrier()                             # data-parallel ranks arrive here with minutes of skew (host TO solves)
         graph = getattr(self, 'update_graph', None)
-        if graph is None and self.use_update_graph:     # the update as a replayed CUDA graph (built once per batch size): at the
-            graph = self.update_graph = self.make_update_graph(self.conf.BATCH_SIZE)       # conf batches it is launch-latency bound
+        world = self.dist.get_world_size() if self.dist is not None else 1
+        # the update as a replayed CUDA graph (built once per batch size): at the conf batches it is launch-latency bound.  With the
+        # NCCL all-reduce fallback (no peer memory) the update stays eager: a collective inside a capture ties the graph to the communicator
+        if graph is None and self.use_update_graph and (world == 1 or self._peer is not None):
+            graph = self.update_graph = self.make_update_graph(self.conf.BATCH_SIZE)
         if graph is not None and graph.B != int(self.conf.BATCH_SIZE):
             graph = self.update_graph = self.make_update_graph(self.conf.BATCH_SIZE)
         for _ in range(int(self.conf.UPDATE_LOOPS[ep])):
