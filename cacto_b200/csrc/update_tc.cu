@@ -956,23 +956,52 @@ struct WgSmem {
   uint32_t tmem_base;
 };
 
-// One float4 of a ws4 tensor = 4 features of one sample: split and scatter as 2-byte elements into the K-major images (k = sample).
-// A warp reads 32 consecutive samples of one feature group (512 contiguous bytes) and writes, per feature, 8 consecutive fp16 into
-// each of 4 k-units that sit in different banks (padded k-unit stride) -- one shared-memory wavefront per store.
-// (First version: one thread gathered 8 samples x 4 features with eight 16-byte loads 128 bytes apart; every load instruction of
-// a warp touched 32 lines, the small L1 beside 198 KB of shared memory thrashed, and the actor's dW2 took 315 us.)
-__device__ __forceinline__ void wg_put(const float4 f, float scale, unsigned char* hi, unsigned char* lo, int lbo, int r, int m0) {
-  const float x[4] = {f.x * scale, f.y * scale, f.z * scale, f.w * scale};
-  const int off0 = (r >> 3) * lbo + (r & 7) * 2;
+// Operand images of a stage, built with stmatrix.trans: a warp takes an 8-feature octet x 32 samples ("unit").  Lane t loads, for each
+// of the four 8-sample octets, the feature PAIR t % 4 of sample t / 4 (8 bytes; the 8 lanes of a pair column read 8 consecutive
+// rows of one ws4 group = one full 128-byte line), scales, splits into fp16 hi / lo, and holds exactly the m8n8 fragment
+// (row = sample, column pair = feature pair) of four matrices; stmatrix.x4.trans writes them transposed -- memory row = feature,
+// 8 consecutive samples = one 16-byte K-major unit (k = sample) -- 512 bytes per instruction.
+// (First version: one thread gathered 8 samples x 4 features with eight 16-byte loads 128 bytes apart; every load instruction of a
+// warp touched 32 lines, the small L1 beside 198 KB of shared memory thrashed, and the actor's dW2 took 315 us.  Second version:
+// coalesced float4 loads and 2-byte scatter stores -- 96 STS.U16 per thread and stage, the issue slots and the shared-memory store
+// wavefronts of the kernel.)
+__device__ __forceinline__ void stsm_x4_trans(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void wg_put_unit(const float2 (&f)[4], float scale, uint32_t hi_addr, uint32_t lo_addr) {
+  uint32_t h[4], l[4];
+#ifdef WG_EXP_NO_CONVERT      // timing experiment only: the loads stay alive through a never-true test
+  if (f[0].x + f[1].x + f[2].x + f[3].x + f[0].y + f[1].y + f[2].y + f[3].y != 12345.678f) return;
+#endif
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + i, off = off0 + (m >> 3) * 128 + (m & 7) * 16;
-    const float h = hi11(x[i]);
-    *reinterpret_cast<__half*>(hi + off) = __float2half_rn(h);
-    *reinterpret_cast<__half*>(lo + off) = __float2half_rn(x[i] - h);
+  for (int m = 0; m < 4; ++m) {
+    const float x0 = f[m].x * scale, x1 = f[m].y * scale;
+    const float h0 = hi11(x0), h1 = hi11(x1);
+    h[m] = pack_h2(h0, h1);
+    l[m] = pack_h2(x0 - h0, x1 - h1);
   }
+  stsm_x4_trans(hi_addr, h);
+  stsm_x4_trans(lo_addr, l);
+}
+// the feature pair (8 F + 2 pr, + 1) of sample `row` of a ws4 tensor; zero beyond its last column group
+__device__ __forceinline__ float2 wg_load_pair(const WgOperand& O, int64_t tile, int feature, int row, int group_limit) {
+  const int g = feature >> 2;
+  if (g >= group_limit) return make_float2(0.f, 0.f);
+#ifdef WG_EXP_NO_LOAD         // timing experiment only
+  return make_float2(1e-3f * (float)row, 1e-3f * (float)feature);
+#endif
+  return __ldg(reinterpret_cast<const float2*>(ws4(O.p, O.W, tile, O.c0 + 4 * g, row)) + ((feature >> 1) & 1));
 }
 
+#ifdef TCU_TRACE   // events of the first CTA of the second-to-last job (a large one in both tables); codes 100+
+#define WGEV(role, code)                                                                                                      \
+  do {                                                                                                                        \
+    if ((int)blockIdx.x == T.cta0[T.njobs - 2] && g_tcu_trace != nullptr && (threadIdx.x & 31) == 0 && tcu_trace_n < TCU_TRACE_N) \
+      g_tcu_trace[(role) * TCU_TRACE_N + tcu_trace_n++] = (clock64() << 8) | (long long)(code);                               \
+  } while (0)
+#else
+#define WGEV(role, code) do { } while (0)
+#endif
 __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const WgTable T, const TcWs ws) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw);
@@ -981,8 +1010,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const WgTable T, const 
   while (ji + 1 < T.njobs && (int)blockIdx.x >= T.cta0[ji + 1]) ++ji;
   const WgJob& J = T.j[ji];
   const int nct = T.cta0[ji + 1] - T.cta0[ji], ci = blockIdx.x - T.cta0[ji];
-  const int64_t t0 = ws.tiles * ci / nct, t1 = ws.tiles * (ci + 1) / nct;
-  const int nstages = (int)(t1 - t0) * J.nterms * (TILE / WG_KS);
+  // the CTAs of a job share its 64-sample half tiles ("units"); a stage = one term of one unit
+  const int64_t units = ws.tiles * (TILE / WG_KS), u0 = units * ci / nct, u1 = units * (ci + 1) / nct;
+  const int nstages = (int)(u1 - u0) * J.nterms;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.full[s], EPI_THREADS); mbar_init(&sm.empty[s], 1); }
     mbar_init(&sm.d_full, 1);
@@ -998,8 +1028,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const WgTable T, const 
   pdl_wait();
   const uint32_t tmem = sm.tmem_base;
   const int N = J.N, lboB = (N / 8) * 128 + 16;
+  TCU_TRACE_DECL;
+#ifdef WG_CTA_TIMES        // debug builds only: [start, end] of every CTA on the global timer (ns)
+  if (tid == 0 && g_tcu_trace != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_tcu_trace[2 * blockIdx.x]));
+#endif
   if (nstages > 0) {
     if (warp < EPI_WARPS) {
+      if (tid == 0) WGEV(0, 100);
       float sx[2], se[2], unscale[2];
       for (int t = 0; t < J.nterms; ++t) {
         float ix, ie;
@@ -1008,46 +1043,67 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const WgTable T, const 
         unscale[t] = ix * ie;
       }
       const int Mg = (J.M + 3) / 4;                       // feature groups of 4 that hold real features
+      const int lane_ = tid & 31, srow = lane_ >> 2, pr = lane_ & 3;       // fragment coordinates: sample within the octet, feature pair
+      const int smat = lane_ >> 3, srow8 = lane_ & 7;                      // stmatrix address duty: row srow8 of matrix smat
+      const int n8 = N / 8, nB = 2 * n8;                                  // B units of a stage
       int st = 0;
       uint32_t ph = 0;
       bool zeroed = false;
-      for (int64_t tile = t0; tile < t1; ++tile)
-        for (int t = 0; t < J.nterms; ++t)
-          for (int half = 0; half < TILE / WG_KS; ++half) {
-            // all loads of the stage are issued before the stage buffer is waited for (the MMAs of the stage two steps back):
-            // A: 32 feature groups x 64 samples = 4 float4 per thread (groups beyond M are zero); B: N / 4 groups x 64 samples <= 8
-            float4 fa[4], fb[8];
+      // stage k of this CTA = (unit u0 + k / nterms, term k % nterms).  All operand loads of a stage are
+      // issued before its buffer is waited for (the MMAs of the stage two steps back).  The stage loop is memory-bound: in-kernel trace
+      // (scratch build with -DTCU_TRACE) of a 96 KB stage = 4 k cycles until the loads are issued (LSU queue full: the SM's share of the
+      // HBM bandwidth is 23 B / cycle) + 2.5 k cycles until the last value has arrived and is converted; issuing the next stage's loads
+      // unit by unit between the conversions (tried) only moves the stall: a warp blocked on a load cannot convert either.
+      float2 fa[2][4], fb[4][4];
+      for (int k = 0; k < nstages; ++k) {
+        const int t = J.nterms == 2 ? (k & 1) : 0;
+        const int64_t unit_ = u0 + (J.nterms == 2 ? (k >> 1) : k), tile = unit_ >> 1;
+        const int row0 = (int)(unit_ & 1) * WG_KS + srow;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int it = tid + j * EPI_THREADS, r = it & (WG_KS - 1), g = it / WG_KS;
-              fa[j] = g < Mg ? __ldg(ws4(J.X[t].p, J.X[t].W, tile, J.X[t].c0 + 4 * g, half * WG_KS + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int u = 0; u < 2; ++u) {
+          const int unit = warp + EPI_WARPS * u, F = unit & 15, h = unit >> 4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int it = tid + j * EPI_THREADS, r = it & (WG_KS - 1), g = it / WG_KS;
-              if (it < (N / 4) * WG_KS)        // (output groups beyond the tensor's width -- padding of a narrow E -- are zero)
-                fb[j] = J.E[t].c0 + 4 * g < J.E[t].W ? __ldg(ws4(J.E[t].p, J.E[t].W, tile, J.E[t].c0 + 4 * g, half * WG_KS + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            mbar_wait(&sm.empty[st], ph ^ 1u);
-            unsigned char *ah = sm.A[st][0], *al = sm.A[st][1], *bh = sm.Bm[st][0], *bl = sm.Bm[st][1];
+          for (int m = 0; m < 4; ++m) fa[u][m] = wg_load_pair(J.X[t], tile, 8 * F + 2 * pr, row0 + 32 * h + 8 * m, Mg);
+        }
+        const int egl = (J.E[t].W - J.E[t].c0 + 3) / 4;            // column groups of E that exist (a narrow E is zero-padded to N)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int it = tid + j * EPI_THREADS, r = it & (WG_KS - 1), g = it / WG_KS;
-              if (g < Mg || !zeroed) wg_put(fa[j], sx[t], ah, al, WG_LBO_A, r, 4 * g);
-            }
+        for (int u = 0; u < 4; ++u) {
+          const int unit = warp + EPI_WARPS * u;
+          if (unit < nB) {
+            const int F = unit % n8, h = unit / n8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int it = tid + j * EPI_THREADS, r = it & (WG_KS - 1), g = it / WG_KS;
-              if (it < (N / 4) * WG_KS) wg_put(fb[j], se[t], bh, bl, lboB, r, 4 * g);
-            }
-            if (st == 1) zeroed = true;          // both stage buffers hold zeros in the feature groups beyond M from now on
-            fence_async_smem();
-            mbar_arrive(&sm.full[st]);
-            if (++st == 2) { st = 0; ph ^= 1u; }
+            for (int m = 0; m < 4; ++m) fb[u][m] = wg_load_pair(J.E[t], tile, 8 * F + 2 * pr, row0 + 32 * h + 8 * m, egl);
           }
+        }
+        if (tid == 0) WGEV(0, 110);          // loads issued
+        mbar_wait(&sm.empty[st], ph ^ 1u);
+        if (tid == 0) WGEV(0, 111);          // stage buffer free
+        const uint32_t ah = smem_u32(sm.A[st][0]), al = smem_u32(sm.A[st][1]), bh = smem_u32(sm.Bm[st][0]), bl = smem_u32(sm.Bm[st][1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int unit = warp + EPI_WARPS * u, F = unit & 15, h = unit >> 4;
+          const uint32_t off = (uint32_t)((4 * h + smat) * WG_LBO_A + F * 128 + srow8 * 16);
+          if (2 * F < Mg || !zeroed) wg_put_unit(fa[u], sx[t], ah + off, al + off);      // octets beyond M stay zero once written
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = warp + EPI_WARPS * u;
+          if (unit < nB) {
+            const int F = unit % n8, h = unit / n8;
+            const uint32_t off = (uint32_t)((4 * h + smat) * lboB + F * 128 + srow8 * 16);
+            wg_put_unit(fb[u], se[t], bh + off, bl + off);
+          }
+        }
+        if (st == 1) zeroed = true;          // both stage buffers hold zeros in the feature octets beyond M from now on
+        fence_async_smem();
+        mbar_arrive(&sm.full[st]);
+        if (tid == 0) WGEV(0, 112);          // converted, published
+        if (++st == 2) { st = 0; ph ^= 1u; }
+      }
       // ---- epilogue: thread <-> feature row; 16-byte vector reductions into the gradient block
       mbar_wait(&sm.d_full, 0u);
       tc_fence_after();
+      if (tid == 0) WGEV(0, 120);                // accumulators complete
       const int wq = warp & 3, cgp = warp >> 2, lane = tid & 31, m = 32 * wq + lane;
       const uint32_t taddr = tmem + ((uint32_t)(32 * wq) << 16);
       for (int ch = cgp; ch < N / 16; ch += 4) {
@@ -1063,25 +1119,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const WgTable T, const 
         // the CTA's partial block [128][N] (plain 64-byte stores; k_tc_wgrad_reduce sums the slices of a job in a fixed order:
         // 16-byte vector reductions straight into dW ran at ~4 per ns chip-wide -- 317 us for the actor's 1.2 M -- and made the
         // gradient bits depend on the arrival order)
-        float4* o = reinterpret_cast<float4*>(ws.PART + ((int64_t)blockIdx.x * TILE + m) * 256 + 16 * ch);
+        // layout [column group of 4][feature row][4]: every store instruction of a warp writes 512 contiguous bytes
+        float4* o = reinterpret_cast<float4*>(ws.PART + (int64_t)blockIdx.x * TILE * 256) + (4 * ch) * TILE + m;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) o[i * TILE] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
+      if (tid == 0) WGEV(0, 121);                // partial block written
       tc_fence_before();
     } else if (warp == EPI_WARPS) {
       const uint32_t idesc = umma_idesc(N);
       int st = 0;
       uint32_t ph = 0;
       int k = 0;
-      for (int64_t tile = t0; tile < t1; ++tile)
-        for (int t = 0; t < J.nterms; ++t)
-          for (int half = 0; half < TILE / WG_KS; ++half, ++k) {
+      for (int64_t unit_ = u0; unit_ < u1; ++unit_)
+        for (int t = 0; t < J.nterms; ++t, ++k) {
             mbar_wait(&sm.full[st], ph);
             tc_fence_after();
+            WGEV(1, 130);                        // stage images present
             if (elect_one()) {
               const uint32_t a_hi = smem_u32(sm.A[st][0]), a_lo = smem_u32(sm.A[st][1]), b_hi = smem_u32(sm.Bm[st][0]), b_lo = smem_u32(sm.Bm[st][1]);
-              const bool first = (tile == t0 && half == 0);
+              const bool first = unit_ == u0;
+#ifdef WG_EXP_NO_MMA           // timing experiment only
+              for (int ks = 0; ks < (first ? 1 : 0); ++ks) {
+#else
               for (int ks = 0; ks < WG_KS / 16; ++ks) {
+#endif
                 const uint64_t ah = umma_desc(a_hi + ks * 2 * WG_LBO_A, WG_LBO_A), al = umma_desc(a_lo + ks * 2 * WG_LBO_A, WG_LBO_A);
                 const uint64_t bh = umma_desc(b_hi + ks * 2 * lboB, lboB), bl = umma_desc(b_lo + ks * 2 * lboB, lboB);
                 const uint32_t d = tmem + (uint32_t)(t * N);
@@ -1099,25 +1161,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const WgTable T, const 
   }
   tc_fence_before();
   __syncthreads();
+#ifdef WG_CTA_TIMES
+  if (tid == 0 && g_tcu_trace != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_tcu_trace[2 * blockIdx.x + 1]));
+#endif
   if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 // dW[m][n] += sum over the CTAs of the job of their partial blocks, in a fixed order (deterministic): 4 lanes per output float4
-// take every 4th slice, then a two-step shuffle tree
+// take every 4th slice, then a two-step shuffle tree.  Consecutive lane quads take consecutive feature rows m of one column group
+// (the partial blocks are [column group][m][4]: 16 contiguous bytes per row)
 __global__ void __launch_bounds__(256) k_tc_wgrad_reduce(const WgTable T, const TcWs ws) {
   pdl_wait();
   const WgJob& J = T.j[blockIdx.y];
   const int n4 = J.N / 4, idx = blockIdx.x * 64 + (threadIdx.x >> 2), part = threadIdx.x & 3;
   const bool live = idx < J.M * n4;
-  const int m = live ? idx / n4 : 0, c = live ? (idx - m * n4) * 4 : 0;
+  const int cg = live ? idx / J.M : 0, m = live ? idx - cg * J.M : 0, c = 4 * cg;
   const int c0 = T.cta0[blockIdx.y], nct = T.cta0[blockIdx.y + 1] - c0;
-  const int64_t tiles = ws.tiles;
+  const int64_t units = ws.tiles * (TILE / WG_KS);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live && c < J.N_real) {
 #pragma unroll 4
     for (int ci = part; ci < nct; ci += 4) {
-      const bool wrote = tiles * ci / nct != tiles * (ci + 1) / nct;        // a CTA without tiles wrote nothing
-      const float4 p = wrote ? __ldg(reinterpret_cast<const float4*>(ws.PART + ((int64_t)(c0 + ci) * TILE + m) * 256 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool wrote = units * ci / nct != units * (ci + 1) / nct;        // a CTA without units wrote nothing
+      const float4 p = wrote ? __ldg(reinterpret_cast<const float4*>(ws.PART + (int64_t)(c0 + ci) * TILE * 256) + cg * TILE + m) : make_float4(0.f, 0.f, 0.f, 0.f);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
   }
@@ -1130,6 +1196,12 @@ __global__ void __launch_bounds__(256) k_tc_wgrad_reduce(const WgTable T, const 
   }
   if (!live || part != 0 || c >= J.N_real) return;
   float* o = J.out + (int64_t)m * J.ld + (int64_t)c * J.ldn;
+  if (J.ldn == 1 && c + 3 < J.N_real && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {      // one 16-byte read-modify-write
+    float4 g = *reinterpret_cast<float4*>(o);
+    g.x += acc.x; g.y += acc.y; g.z += acc.z; g.w += acc.w;
+    *reinterpret_cast<float4*>(o) = g;
+    return;
+  }
   o[0] += acc.x;
   if (c + 1 < J.N_real) o[J.ldn] += acc.y;
   if (c + 2 < J.N_real) o[2 * J.ldn] += acc.z;
@@ -1216,23 +1288,35 @@ static int num_sms() {
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   return n;
 }
-// split `ctas` CTAs over the jobs in proportion to their cost: a stage (64 samples of one term) costs a latency-bound ~0.8 us
-// plus its operand bytes at the SM's share of the memory bandwidth (~40 B / ns): (real feature groups + N / 4) KB
+// Split `ctas` CTAs over the jobs so that the slowest CTA is as fast as possible.  A CTA takes whole units (64-sample half tiles);
+// a unit of a job costs one stage per term, and a stage costs -- per-CTA global-timer stamps of a -DWG_CTA_TIMES build,
+// B = 16 384 -- a latency-bound 1.15 us + 0.034 us per KB of the E operand (N / 4 KB) + next to nothing for the X operand:
+// 1.7 us at N = 64, 2.3 us at N = 128, 3.3-3.4 us at N = 256, whatever M is.  (The first model, 0.8 us + bytes at 40 B / ns
+// over whole tiles, gave the 7 x 64 job of the critic 22 CTAs that ran 43 us beside 32 us for the rest.)
 static void wg_assign(WgTable& T, int ctas, int64_t tiles) {
-  double cost[8], total = 0;
-  for (int j = 0; j < T.njobs; ++j) {
-    const double kb = (T.j[j].M + 3) / 4 + T.j[j].N / 4;
-    cost[j] = T.j[j].nterms * (0.8 + kb * 1024 / 40e3);
-    total += cost[j];
+  const int64_t units = tiles * (TILE / WG_KS);
+  double unit_cost[8];
+  for (int j = 0; j < T.njobs; ++j) unit_cost[j] = T.j[j].nterms * (1.15 + 0.034 * (T.j[j].N / 4) + 0.004 * ((T.j[j].M + 3) / 4));
+  // smallest makespan for which the CTAs suffice: job j needs ceil(units / floor(makespan / unit_cost[j])) CTAs
+  auto need = [&](double span) {
+    int64_t total = 0;
+    for (int j = 0; j < T.njobs; ++j) {
+      const int64_t per = (int64_t)(span / unit_cost[j]);
+      if (per < 1) return (int64_t)1 << 40;
+      total += (units + per - 1) / per;
+    }
+    return total;
+  };
+  double lo = 0, hi = 0;
+  for (int j = 0; j < T.njobs; ++j) hi = hi > unit_cost[j] * (double)(units + 1) ? hi : unit_cost[j] * (double)(units + 1);     // one CTA per job
+  for (int it = 0; it < 48; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (need(mid) <= ctas) hi = mid; else lo = mid;
   }
-  int used = 0;
   T.cta0[0] = 0;
   for (int j = 0; j < T.njobs; ++j) {
-    int64_t n = (int64_t)(ctas * cost[j] / total);
-    if (n < 1) n = 1;
-    if (n > tiles) n = tiles;
-    used += (int)n;
-    T.cta0[j + 1] = used;
+    const int64_t per = (int64_t)(hi / unit_cost[j]);
+    T.cta0[j + 1] = T.cta0[j] + (int)((units + per - 1) / per);
   }
 }
 static int launch_wgrad(WgTable& WT, const TcWs& ws, int sms, cudaStream_t st) {
