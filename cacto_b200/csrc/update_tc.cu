@@ -1167,13 +1167,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_wgrad(const WgTable T, const 
   if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
-// dW[m][n] += sum over the CTAs of the job of their partial blocks, in a fixed order (deterministic): 4 lanes per output float4
-// take every 4th slice, then a two-step shuffle tree.  Consecutive lane quads take consecutive feature rows m of one column group
-// (the partial blocks are [column group][m][4]: 16 contiguous bytes per row)
+// dW[m][n] += sum over the CTAs of the job of their partial blocks, in a fixed order (deterministic): WGR_LANES lanes per output
+// float4 take every WGR_LANES-th slice, then a shuffle tree.  Consecutive lane groups take consecutive feature rows m of one column
+// group (the partial blocks are [column group][m][4]: 16 contiguous bytes per row)
+constexpr int WGR_LANES = 16, WGR_OUT = 256 / WGR_LANES;         // lanes per output, outputs per block
 __global__ void __launch_bounds__(256) k_tc_wgrad_reduce(const WgTable T, const TcWs ws) {
   pdl_wait();
   const WgJob& J = T.j[blockIdx.y];
-  const int n4 = J.N / 4, idx = blockIdx.x * 64 + (threadIdx.x >> 2), part = threadIdx.x & 3;
+  const int n4 = J.N / 4, idx = blockIdx.x * WGR_OUT + (threadIdx.x / WGR_LANES), part = threadIdx.x % WGR_LANES;
   const bool live = idx < J.M * n4;
   const int cg = live ? idx / J.M : 0, m = live ? idx - cg * J.M : 0, c = 4 * cg;
   const int c0 = T.cta0[blockIdx.y], nct = T.cta0[blockIdx.y + 1] - c0;
@@ -1181,14 +1182,14 @@ __global__ void __launch_bounds__(256) k_tc_wgrad_reduce(const WgTable T, const 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live && c < J.N_real) {
 #pragma unroll 4
-    for (int ci = part; ci < nct; ci += 4) {
+    for (int ci = part; ci < nct; ci += WGR_LANES) {
       const bool wrote = units * ci / nct != units * (ci + 1) / nct;        // a CTA without units wrote nothing
       const float4 p = wrote ? __ldg(reinterpret_cast<const float4*>(ws.PART + (int64_t)(c0 + ci) * TILE * 256) + cg * TILE + m) : make_float4(0.f, 0.f, 0.f, 0.f);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
   }
 #pragma unroll
-  for (int o = 1; o < 4; o <<= 1) {
+  for (int o = 1; o < WGR_LANES; o <<= 1) {
     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
     acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
@@ -1328,7 +1329,7 @@ static int launch_wgrad(WgTable& WT, const TcWs& ws, int sms, cudaStream_t st) {
   CACTO_LAUNCH_CHECK();
   int maxel = 0;
   for (int j = 0; j < WT.njobs; ++j) maxel = maxel > WT.j[j].M * (WT.j[j].N / 4) ? maxel : WT.j[j].M * (WT.j[j].N / 4);
-  if (cudaError_t le_ = launch_tc(k_tc_wgrad_reduce, dim3(dim3((maxel + 63) / 64, WT.njobs)), 256, 0, st, WT, ws)) return (int)le_;
+  if (cudaError_t le_ = launch_tc(k_tc_wgrad_reduce, dim3((maxel + WGR_OUT - 1) / WGR_OUT, WT.njobs), 256, 0, st, WT, ws)) return (int)le_;
   CACTO_LAUNCH_CHECK();
   return 0;
 }
