@@ -30,6 +30,15 @@ def test_ops_reject_bad_arguments_without_a_gpu():
         torch.ops.cacto.dyn_step(P, 0, s, a, torch.empty_like(s))               # host tensors: no CPU fallback
     with pytest.raises(RuntimeError):
         torch.ops.cacto.dyn_step(P[:-1].clone(), 0, s, a, torch.empty_like(s))  # truncated parameter block
+    # element counts are checked by the shim (the C ABI takes bare pointers): an undersized output never reaches a kernel
+    with pytest.raises(RuntimeError, match='out has 21 elements, expected 28'):
+        torch.ops.cacto.dyn_step(P, 0, s, a, torch.empty((3, 7)))
+    with pytest.raises(RuntimeError, match=r'state must be \[B\]\[7\]'):
+        torch.ops.cacto.dyn_step(P, 0, torch.zeros((4, 6)), a, torch.empty((4, 6)))
+    with pytest.raises(RuntimeError, match='states has'):
+        torch.ops.cacto.rollout(P, None, 0, torch.zeros((4, 7), dtype=torch.float64), torch.zeros(4, dtype=torch.int32), 10,
+                                torch.empty((10, 7, 4), dtype=torch.float64), torch.empty((10, 3, 4), dtype=torch.float64),
+                                torch.empty(4, dtype=torch.int32), None)
 
 
 @pytest.mark.gpu
@@ -53,9 +62,12 @@ def test_op_and_ctypes_binding_agree_bit_for_bit():
     with pytest.raises(RuntimeError, match='sizeof'):
         torch.ops.cacto.dyn_step(env._pt[:-1].clone(), 0, s, a, torch.empty_like(s))
     ws = torch.empty(16, dtype=torch.uint8, device='cuda')
-    z = torch.zeros(256 * 8, device='cuda')
-    with pytest.raises(RuntimeError, match='bad size'):
-        torch.ops.cacto.actor_grad_tc(env._pt, z, z, z, torch.zeros(256, dtype=torch.float64, device='cuda'), 1.0, z.clone(), None, ws)
+    na_, nc_ = int(lib.cacto_actor_param_count(7, 3)), int(lib.cacto_critic_param_count(7))
+    act, cri, st = torch.zeros(na_, device='cuda'), torch.zeros(nc_, device='cuda'), torch.zeros((256, 7), device='cuda')
+    with pytest.raises(RuntimeError, match='workspace has 16 elements'):
+        torch.ops.cacto.actor_grad_tc(env._pt, act, cri, st, torch.zeros(256, dtype=torch.float64, device='cuda'), 1.0, act.clone(), None, ws)
+    with pytest.raises(RuntimeError, match='grad has'):
+        torch.ops.cacto.actor_grad_tc(env._pt, act, cri, st, torch.zeros(256, dtype=torch.float64, device='cuda'), 1.0, act[:-1].clone(), None, ws)
 
 
 @pytest.mark.gpu
