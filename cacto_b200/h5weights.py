@@ -17,7 +17,8 @@ _LAYOUT_MSG = re.compile(rb'\x08\x00\x18\x00.\x00\x00\x00\x03\x01', re.S)
 
 def read_datasets(path):
     """All contiguous float32 datasets of the file, in object-header order, paired as (kernel, bias)."""
-    blob = open(path, 'rb').read()
+    with open(path, 'rb') as f:
+        blob = f.read()
     data = []
     for m in _LAYOUT_MSG.finditer(blob):
         addr, size = struct.unpack('<QQ', blob[m.end():m.end() + 16])
@@ -182,7 +183,8 @@ def read_tree(path):
     """Walk a classic-format HDF5 file the way libhdf5 does (superblock -> root symbol-table entry -> object headers -> B-tree ->
     symbol nodes -> local heap) and return {'attrs': {path: {name: value}}, 'datasets': {path: float32 array}}.  Handles what Keras
     weight files contain: fixed- or variable-length string attributes, contiguous little-endian float32 datasets."""
-    b = open(path, 'rb').read()
+    with open(path, 'rb') as f:
+        b = f.read()
     assert b[:8] == b'\x89HDF\r\n\x1a\n' and b[8] == 0 and b[13] == 8 and b[14] == 8, 'not a superblock-v0 HDF5 file with 8-byte offsets'
 
     def messages(addr):

@@ -185,12 +185,15 @@ def bind_to_gpu_numa_node(device_index):
         import torch
         p = torch.cuda.get_device_properties(device_index)
         bdf = '%04x:%02x:%02x.0' % (int(getattr(p, 'pci_domain_id', 0)), int(p.pci_bus_id), int(p.pci_device_id))
-        node = int(open(f'/sys/bus/pci/devices/{bdf}/numa_node').read())
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as f:
+            node = int(f.read())
         info['numa_node'] = node
         if node < 0:
             return info
         cpus = set()
-        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpulist = f.read().strip()
+        for part in cpulist.split(','):
             lo, _, hi = part.partition('-')
             cpus.update(range(int(lo), int(hi or lo) + 1))
         allowed = cpus & os.sched_getaffinity(0)
