@@ -132,23 +132,25 @@ class RL_AC:
             self.peer_barrier()
         world = self.dist.get_world_size() if self.dist is not None else 1
         gb = state_batch.shape[0] * world
+        # the learning-rate schedules / step counters of both Adam steps in one launch (every launch on this path is ~3 us)
+        type(self.critic_optimizer).prepare_pair(self.critic_optimizer, self.actor_optimizer, self.critic_model.params.device)
         critic_grad, reward_to_go_batch, critic_value, target_critic_value = self.NN.compute_critic_grad(
             self.critic_model, self.target_critic, state_batch, state_next_rollout_batch, partial_reward_to_go_batch, dVdx_batch, d_batch,
             weights_batch, global_batch=gb)
         if world > 1:
             fused = fuse_target and not self.conf.MC
             self._reduce_and_step(self.critic_optimizer, self.critic_model, self.actor_model, self.target_critic if fused else None,
-                                  self.conf.UPDATE_RATE if fused else 0.0)
+                                  self.conf.UPDATE_RATE if fused else 0.0, prepared=True)
         elif fuse_target and not self.conf.MC:
-            self.critic_optimizer.step(self.critic_model, target=self.target_critic, tau=self.conf.UPDATE_RATE)
+            self.critic_optimizer.step(self.critic_model, target=self.target_critic, tau=self.conf.UPDATE_RATE, prepared=True)
         else:
-            self.critic_optimizer.apply_gradients(zip(critic_grad, self.critic_model.trainable_variables))
+            self.critic_optimizer.apply_gradients(zip(critic_grad, self.critic_model.trainable_variables), prepared=True)
 
         actor_grad = self.NN.compute_actor_grad(self.actor_model, self.critic_model, state_batch, term_batch, batch_size, global_batch=gb)
         if world > 1:
-            self._reduce_and_step(self.actor_optimizer, self.actor_model, self.critic_model)
+            self._reduce_and_step(self.actor_optimizer, self.actor_model, self.critic_model, prepared=True)
         else:
-            self.actor_optimizer.apply_gradients(zip(actor_grad, self.actor_model.trainable_variables))
+            self.actor_optimizer.apply_gradients(zip(actor_grad, self.actor_model.trainable_variables), prepared=True)
         return reward_to_go_batch, critic_value, target_critic_value
 
     # ------------------------------------------------------------------------------ CUDA-graph update
@@ -160,14 +162,13 @@ class RL_AC:
         B = io['state'].shape[0]
         inv_B = 1.0 / float(B * world)
         cm, tc, am = self.critic_model, self.target_critic, self.actor_model
-        self.critic_optimizer.prepare(cm.params.device, zero=nn.last_critic_loss)
+        type(self.critic_optimizer).prepare_pair(self.critic_optimizer, self.actor_optimizer, cm.params.device, zero=nn.last_critic_loss)
         nn.launch_critic_grad(cm, tc, io['state'], io['state_next'], io['partial_rtg'], io['dVdx'], io['done'], io['weights'], inv_B,
                               io['rtg'], io['V'], io['V_target'], B)
         if c.MC:
             self._reduce_and_step(self.critic_optimizer, cm, am, prepared=True)
         else:
             self._reduce_and_step(self.critic_optimizer, cm, am, target=tc, tau=c.UPDATE_RATE, prepared=True)
-        self.actor_optimizer.prepare(am.params.device)
         nn.launch_actor_grad(am, cm, io['state'], io['term'], inv_B, None, B)
         self._reduce_and_step(self.actor_optimizer, am, cm, prepared=True)
 

@@ -132,6 +132,8 @@ _SIGNATURES = {
                              [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_actor_grad_tc': (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     'cacto_adam_schedule': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'cacto_adam_schedule2': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     'cacto_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p] + [C.c_float] * 3 + [C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int64, C.c_void_p]),
     'cacto_transpose_params': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -201,6 +201,17 @@ void adam_schedule(Tensor step, const Tensor& boundaries, const Tensor& values, 
   ok(cacto_adam_schedule((int64_t*)dev(step, at::kLong, "step"), (const float*)dev(boundaries, F32, "boundaries"), (const float*)dev(values, F32, "values"), (int32_t)nb,
                          (float)beta1, (float)beta2, (float*)dev(alpha, F32, "alpha"), (float*)opt(zero, F32, "zero"), stream()), "adam_schedule");
 }
+void adam_schedule2(Tensor step_a, const Tensor& boundaries_a, const Tensor& values_a, int64_t nb_a, double beta1_a, double beta2_a, Tensor alpha_a, Tensor step_b,
+                    const Tensor& boundaries_b, const Tensor& values_b, int64_t nb_b, double beta1_b, double beta2_b, Tensor alpha_b, const optional<Tensor>& zero) {
+  TORCH_CHECK(nb_a >= 0 && nb_b >= 0, "cacto: nb < 0");
+  need(step_a, 1, "step_a"); need_at_least(boundaries_a, nb_a, "boundaries_a"); need_at_least(values_a, nb_a + 1, "values_a"); need(alpha_a, 1, "alpha_a");
+  need(step_b, 1, "step_b"); need_at_least(boundaries_b, nb_b, "boundaries_b"); need_at_least(values_b, nb_b + 1, "values_b"); need(alpha_b, 1, "alpha_b");
+  need(zero, 1, "zero");
+  ok(cacto_adam_schedule2((int64_t*)dev(step_a, at::kLong, "step_a"), (const float*)dev(boundaries_a, F32, "boundaries_a"), (const float*)dev(values_a, F32, "values_a"),
+                          (int32_t)nb_a, (float)beta1_a, (float)beta2_a, (float*)dev(alpha_a, F32, "alpha_a"), (int64_t*)dev(step_b, at::kLong, "step_b"),
+                          (const float*)dev(boundaries_b, F32, "boundaries_b"), (const float*)dev(values_b, F32, "values_b"), (int32_t)nb_b, (float)beta1_b, (float)beta2_b,
+                          (float*)dev(alpha_b, F32, "alpha_b"), (float*)opt(zero, F32, "zero"), stream()), "adam_schedule2");
+}
 void adam_step(Tensor params, Tensor grad, Tensor m, Tensor v, double alpha_t, const optional<Tensor>& alpha_dev, double beta1, double beta2, double eps,
                const optional<Tensor>& target, double tau, const optional<Tensor>& params_T, int64_t is_critic, int64_t ns, int64_t na) {
   const int64_t n = params.numel();
@@ -278,6 +289,8 @@ TORCH_LIBRARY(cacto, m) {
   m.def("actor_grad_tc(Tensor p, Tensor actor, Tensor critic, Tensor state, Tensor term, float inv_B, Tensor(a!) grad, Tensor(b!)? actions, Tensor(c!) workspace) -> ()",
         actor_grad_tc);
   m.def("adam_schedule(Tensor(a!) step, Tensor boundaries, Tensor values, int nb, float beta1, float beta2, Tensor(b!) alpha, Tensor(c!)? zero) -> ()", adam_schedule);
+  m.def("adam_schedule2(Tensor(a!) step_a, Tensor boundaries_a, Tensor values_a, int nb_a, float beta1_a, float beta2_a, Tensor(b!) alpha_a, Tensor(c!) step_b, "
+        "Tensor boundaries_b, Tensor values_b, int nb_b, float beta1_b, float beta2_b, Tensor(d!) alpha_b, Tensor(e!)? zero) -> ()", adam_schedule2);
   m.def("adam_step(Tensor(a!) params, Tensor(b!) grad, Tensor(c!) m, Tensor(d!) v, float alpha_t, Tensor? alpha_dev, float beta1, float beta2, float eps, "
         "Tensor(e!)? target, float tau, Tensor(f!)? params_T, int is_critic, int ns, int na) -> ()", adam_step);
   m.def("transpose_params(Tensor params, Tensor(a!) params_T, int is_critic, int ns, int na) -> ()", transpose_params);

@@ -1054,6 +1054,35 @@ __global__ void k_adam_schedule(long long* __restrict__ step, const float* __res
   if (zero_me != nullptr) zero_me[0] = 0.f;
 }
 
+// the schedules of the two optimizers of an update in ONE launch (a one-thread kernel costs a launch slot of ~2.7 us on the
+// update's critical path, whatever it computes): lane 0 of warp 0 serves the first optimizer, lane 0 of warp 1 the second
+struct AdamSched { long long* step; const float* boundaries; const float* values; int nb; float beta1, beta2; float* alpha_out; };
+__global__ void k_adam_schedule2(AdamSched a, AdamSched b, float* __restrict__ zero_me) {
+  pdl_wait();
+  if (blockIdx.x != 0 || (threadIdx.x & 31) != 0 || threadIdx.x >= 64) return;
+  const AdamSched& S = threadIdx.x == 0 ? a : b;
+  const long long it = S.step[0];
+  int k = 0;
+  for (int i = 0; i < S.nb; ++i) k += (S.boundaries[i] < (float)it) ? 1 : 0;
+  const float t = (float)(it + 1);
+  S.alpha_out[0] = S.values[k] * sqrtf(1.f - powf(S.beta2, t)) / (1.f - powf(S.beta1, t));
+  S.step[0] = it + 1;
+  if (threadIdx.x == 0 && zero_me != nullptr) zero_me[0] = 0.f;
+}
+
+extern "C" int cacto_adam_schedule2(int64_t* step_a, const float* boundaries_a, const float* values_a, int32_t nb_a, float beta1_a, float beta2_a,
+                                    float* alpha_a, int64_t* step_b, const float* boundaries_b, const float* values_b, int32_t nb_b, float beta1_b,
+                                    float beta2_b, float* alpha_b, float* zero_or_null, void* stream) {
+  if (!step_a || !values_a || !alpha_a || (nb_a > 0 && !boundaries_a) || nb_a < 0) return CACTO_E_ARG;
+  if (!step_b || !values_b || !alpha_b || (nb_b > 0 && !boundaries_b) || nb_b < 0) return CACTO_E_ARG;
+  if (step_a == step_b || alpha_a == alpha_b) return CACTO_E_ARG;
+  AdamSched A = {reinterpret_cast<long long*>(step_a), boundaries_a, values_a, nb_a, beta1_a, beta2_a, alpha_a};
+  AdamSched Bs = {reinterpret_cast<long long*>(step_b), boundaries_b, values_b, nb_b, beta1_b, beta2_b, alpha_b};
+  if (cudaError_t le = launch_pdl(k_adam_schedule2, 1, 64, 0, (cudaStream_t)stream, A, Bs, zero_or_null)) return (int)le;
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int cacto_adam_schedule(int64_t* step, const float* boundaries, const float* values, int32_t nb, float beta1, float beta2,
                                    float* alpha_out, float* zero_or_null, void* stream) {
   if (!step || !values || !alpha_out || (nb > 0 && !boundaries) || nb < 0) return CACTO_E_ARG;

@@ -64,6 +64,13 @@ class Adam:
         d = self._device_state(device)
         ops.adam_schedule(d['step'], d['boundaries'], d['values'], d['nb'], self.beta_1, self.beta_2, d['alpha'], zero)
 
+    @staticmethod
+    def prepare_pair(first, second, device, zero=None):
+        """``first.prepare(device, zero)`` and ``second.prepare(device)`` in ONE launch (the two optimizers of RL_AC.update)."""
+        a, b = first._device_state(device), second._device_state(device)
+        ops.adam_schedule2(a['step'], a['boundaries'], a['values'], a['nb'], first.beta_1, first.beta_2, a['alpha'],
+                           b['step'], b['boundaries'], b['values'], b['nb'], second.beta_1, second.beta_2, b['alpha'], zero)
+
     def step(self, net, target=None, tau=0.0, prepared=False, peer=None, zero_other=None):
         """One Adam step on ``net`` from ``net.grad`` (zeroed afterwards); optionally the Polyak update
         ``target = tau * net + (1 - tau) * target`` (RL.py:113-118) in the same launch.
@@ -87,8 +94,9 @@ class Adam:
                           float(tau), net.params_T, net.is_critic, net.ns, net.na)
         self.iterations += 1
 
-    def apply_gradients(self, grads_and_vars):
-        """Keras signature: ``apply_gradients(zip(grads, model.trainable_variables))``."""
+    def apply_gradients(self, grads_and_vars, prepared=False):
+        """Keras signature: ``apply_gradients(zip(grads, model.trainable_variables))``.  ``prepared``: the schedule kernel of this
+        step has been launched already (``prepare`` / ``prepare_pair``)."""
         grads, variables = zip(*list(grads_and_vars))
         net = Network._registry.get(variables[0].data_ptr())
         if net is None:
@@ -96,4 +104,4 @@ class Adam:
         if grads[0].data_ptr() != net.grad.data_ptr():          # foreign gradients: stage them into the accumulator
             for dst, g in zip(net._grad_views, grads):
                 dst.copy_(torch.as_tensor(g).to(dst.device, dst.dtype))
-        self.step(net)
+        self.step(net, prepared=prepared)

@@ -247,6 +247,11 @@ int cacto_adam_step(float* params, float* grad, float* m, float* v, float alpha_
  * RL.py:82-85; nb = 0 for a constant rate values[0]), increments the counter and clears zero_or_null[0]. */
 int cacto_adam_schedule(int64_t* step, const float* boundaries, const float* values, int32_t nb, float beta1,
                         float beta2, float* alpha_out, float* zero_or_null, void* stream);
+/* The same for the two optimizers of an update (critic: _a, actor: _b) in one launch: RL_AC.update runs both Adam steps
+ * (RL.py:101-111), and at the reference's batch of 64 every launch on the update's critical path is 4 % of it. */
+int cacto_adam_schedule2(int64_t* step_a, const float* boundaries_a, const float* values_a, int32_t nb_a, float beta1_a,
+                         float beta2_a, float* alpha_a, int64_t* step_b, const float* boundaries_b, const float* values_b,
+                         int32_t nb_b, float beta1_b, float beta2_b, float* alpha_b, float* zero_or_null, void* stream);
 
 /* ---- Data-parallel update (the reference is single-GPU, main.py:59): cacto_adam_step with the gradient
  *      all-reduce fused in over NVLink peer memory.  peer_grads[r] / peer_flags[r] (HOST arrays of `world` device pointers)
