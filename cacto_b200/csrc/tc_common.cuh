@@ -28,6 +28,8 @@ constexpr int CHUNK_ELEMS = 4096;               // N * kc of one weight chunk
 constexpr int CHUNK_BYTES = 4 * CHUNK_ELEMS;    // hi + lo fp16 images: 16 KB
 constexpr int LBO_A = (TILE / 8) * 128;         // k-unit stride of a 128-row K-major image: 2048 B
 constexpr int MAX_LAYERS = 6;
+constexpr int A_GROUP_K = 64, A_GROUPS = 4;     // the A image of a layer is published in groups of 64 k-values (<= 256 / 64 groups)
+constexpr int ACC_COLS = 256;                   // TMEM columns of one accumulator; consecutive layers alternate between two
 constexpr float SIN_SCALE = 8192.f;             // |sin|, |cos| <= 1 -> |a'| <= 2^13
 
 struct LayerSeq {        // the layers of one chain, in issue order; K, N multiples of 16, N <= 256
@@ -196,15 +198,16 @@ struct ChainSmem {
   alignas(1024) unsigned char a_lo[A_IMG];
   alignas(16) float rowx[2][4][TILE];                                // per-row exchange between the 4 column groups (double-buffered)
   alignas(16) float colsum[640];                                     // per-CTA column sums (bias / head gradients), flushed at the end
-  uint64_t w_full[RING], w_empty[RING], a_full, d_full;
+  uint64_t w_full[RING], w_empty[RING], a_full[A_GROUPS], d_full;
   uint32_t tmem_base;
 };
 
 // what an epilogue thread knows about itself
 struct Epi {
   int warp, lane, q, cgp, row;        // TMEM lane quadrant, column group, row within the tile
-  uint32_t taddr;                     // TMEM address of (row, column 0)
-  uint32_t layers_done;               // accumulators consumed so far (phase of d_full)
+  uint32_t taddr;                     // TMEM address of (row, column 0) of the accumulator being consumed (set by wait_acc)
+  uint32_t tbase;                     // ... of accumulator buffer 0
+  uint32_t layers_done;               // accumulators consumed so far (phase of d_full, accumulator buffer = parity)
   uint32_t xbuf;                      // parity of the row-exchange buffer
 };
 
@@ -212,13 +215,13 @@ template <typename SM>
 __device__ __forceinline__ void chain_setup(SM& sm, int tid, int warp) {
   if (tid == 0) {
     for (int s = 0; s < (int)(sizeof(sm.w_full) / 8); ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], 1); }
-    mbar_init(&sm.a_full, EPI_THREADS);
+    for (int g = 0; g < A_GROUPS; ++g) mbar_init(&sm.a_full[g], EPI_THREADS);
     mbar_init(&sm.d_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 640; i += THREADS) sm.colsum[i] = 0.f;
   if (warp == EPI_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(2 * ACC_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -229,25 +232,40 @@ template <typename SM>
 __device__ __forceinline__ void chain_teardown(SM& sm, int warp) {
   tc_fence_before();
   __syncthreads();
-  if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(256));
+  if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(2 * ACC_COLS));
 }
 __device__ __forceinline__ Epi epi_init(int tid, uint32_t tmem) {
   Epi e;
   e.warp = tid >> 5; e.lane = tid & 31; e.q = e.warp & 3; e.cgp = e.warp >> 2; e.row = 32 * e.q + e.lane;
-  e.taddr = tmem + ((uint32_t)(32 * e.q) << 16);
+  e.tbase = tmem + ((uint32_t)(32 * e.q) << 16);
+  e.taddr = e.tbase;
   e.layers_done = 0; e.xbuf = 0;
   return e;
 }
-// the A image of the next layer is complete (and my TMEM reads of the previous accumulator are done)
+// The A image of the next layer reaches the issuer in groups of A_GROUP_K k-values: the issuer starts the UMMAs of a K-chunk as
+// soon as its groups are complete, while the epilogue threads are still producing the later ones (the accumulators of consecutive
+// layers alternate between two TMEM buffers, so the running UMMAs never touch the one being read).  Every epilogue thread
+// arrives exactly once per layer on EACH of the A_GROUPS barriers -- publish_a_group(g) as soon as its share of group g is
+// written, publish_a_from(g) for all remaining groups -- so that all of them flip once per layer whatever the layer's width.
 template <typename SM>
-__device__ __forceinline__ void publish_a(SM& sm) {
+__device__ __forceinline__ void publish_a_group(SM& sm, int g) {
   fence_async_smem();
   tc_fence_before();
-  mbar_arrive(&sm.a_full);
+  mbar_arrive(&sm.a_full[g]);
 }
+template <typename SM>
+__device__ __forceinline__ void publish_a_from(SM& sm, int g0) {
+  fence_async_smem();
+  tc_fence_before();
+  for (int g = g0; g < A_GROUPS; ++g) mbar_arrive(&sm.a_full[g]);
+}
+// the whole A image of the next layer is complete (and my TMEM reads of the previous accumulator are done)
+template <typename SM>
+__device__ __forceinline__ void publish_a(SM& sm) { publish_a_from(sm, 0); }
 template <typename SM>
 __device__ __forceinline__ void wait_acc(SM& sm, Epi& e) {
   mbar_wait(&sm.d_full, e.layers_done & 1u);
+  e.taddr = e.tbase + (e.layers_done & 1u) * (uint32_t)ACC_COLS;
   ++e.layers_done;
   tc_fence_after();
 }
@@ -347,10 +365,13 @@ __device__ __forceinline__ void issue_job(SM& sm, const LayerSeq& L, RingState& 
   for (int l = 0; l < L.n; ++l) {
     const int K = L.K[l], N = L.N[l], kc = layer_kc(K, N), nch = K / kc;
     const uint32_t idesc = umma_idesc(N), lboB = (uint32_t)(N / 8) * 128u, b_lo = (uint32_t)(N * kc * 2);
-    mbar_wait(&sm.a_full, rs.layers & 1u);
+    const uint32_t par = rs.layers & 1u, d = tmem + par * (uint32_t)ACC_COLS;      // a_full phase and accumulator buffer of this layer
     ++rs.layers;
-    TCU_EV(1, 1);                          // A image present
+    int groups = 0;                        // A groups waited for so far
     for (int c = 0; c < nch; ++c) {
+      const int need = ((c + 1) * kc - 1) / A_GROUP_K + 1;      // groups that hold the k-values of this chunk
+      for (; groups < need; ++groups) mbar_wait(&sm.a_full[groups], par);
+      if (c == 0) TCU_EV(1, 1);            // first A group present
       mbar_wait(&sm.w_full[rs.slot], rs.phase);
       if (c == 0) TCU_EV(1, 2);            // first weight chunk present
       tc_fence_after();
@@ -360,9 +381,9 @@ __device__ __forceinline__ void issue_job(SM& sm, const LayerSeq& L, RingState& 
           const uint32_t ao = (uint32_t)((c * kc + 16 * ks) >> 3) * LBO_A, bo = b0 + (uint32_t)ks * 2u * lboB;
           const uint64_t ah = umma_desc(a_hi + ao, LBO_A), al = umma_desc(a_lo + ao, LBO_A);
           const uint64_t bh = umma_desc(bo, lboB), bl = umma_desc(bo + b_lo, lboB);
-          umma_f16(tmem, ah, bh, idesc, (c == 0 && ks == 0) ? 0u : 1u);
-          umma_f16(tmem, ah, bl, idesc, 1u);
-          umma_f16(tmem, al, bh, idesc, 1u);
+          umma_f16(d, ah, bh, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+          umma_f16(d, ah, bl, idesc, 1u);
+          umma_f16(d, al, bh, idesc, 1u);
         }
         umma_commit(&sm.w_empty[rs.slot]);
         if (c == nch - 1) umma_commit(&sm.d_full);

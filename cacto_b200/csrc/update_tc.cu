@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_critic_fwd(const __grid_const
           if (CSp != nullptr) ws_store16(CSp, CWT, tile, col0 + 16 * ch, e.row, c);
           if (l < 3) {
             put_a16(sm, e, 16 * ch, s, SIN_SCALE);
+            publish_a_group(sm, ch >> 2);             // the next layer's UMMAs start on this 64-column group
           } else if (w5 != nullptr) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_critic_fwd(const __grid_const
           }
         }
         FEV(32);
-        if (l < 3) publish_a(sm);
+        if (l < 3) publish_a_from(sm, N / A_GROUP_K);
         FEV(33);
       }
       if (kind != FWD_FP) {
@@ -533,13 +534,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_critic_bwd(const __grid_const
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fabsf(v[i]));
-            if (!(MODE == BWD_B && lo == 0)) put_a16(sm, e, 16 * ch, v, s);
+            if (!(MODE == BWD_B && lo == 0)) {
+              put_a16(sm, e, 16 * ch, v, s);
+              publish_a_group(sm, j);
+            }
           }
         if (MODE == BWD_G) amax_update(ws.amax + AM_DL, mx, e.lane);
         if (MODE == BWD_B) amax_update(ws.amax + AM_EE, mx, e.lane);
         rinv = rnew;
         EEV(24);             // chunks done
-        if (!(MODE == BWD_B && lo == 0)) publish_a(sm);
+        if (!(MODE == BWD_B && lo == 0)) publish_a_from(sm, nch);
         EEV(25);
       }
 
@@ -581,13 +585,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_critic_bwd(const __grid_const
             for (int j = 0; j < 16; ++j) d3[j] = 0.f;
             if (valid) {
               const int ns = P.ns, na = P.na;
+              float gs[CACTO_MAX_NS];                                        // dV/ds' in raw state units (one division per state, not per (state, action))
+#pragma unroll
+              for (int k = 0; k < CACTO_MAX_NS; ++k) gs[k] = k < ns ? normalize_scale(P, k) * g0[k] : 0.f;
 #pragma unroll
               for (int j = 0; j < CACTO_MAX_NA; ++j)
                 if (j < na) {
                   float qv = ws.DRDA[b * na + j];
 #pragma unroll
                   for (int k = 0; k < CACTO_MAX_NS; ++k)
-                    if (k < ns) qv = fmaf(normalize_scale(P, k) * g0[k], ws.FU[(b * ns + k) * na + j], qv);
+                    if (k < ns) qv = fmaf(gs[k], ws.FU[(b * ns + k) * na + j], qv);
                   d3[j] = -qv * A.inv_B;
                   m = fmaxf(m, fabsf(d3[j]));
                 }
@@ -707,6 +714,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_critic_adj(const __grid_const
             if (l < 3) {
               ws_store16(ws.AA, 256, tile, col0 + 16 * ch, e.row, v);
               put_a16(sm, e, 16 * ch, v, s);
+              publish_a_group(sm, j);
             } else {
               warp_colsum16(sm.colsum, 16 * ch, v, e.lane);                  // d w5 += sum_s a_4
             }
@@ -715,7 +723,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_critic_adj(const __grid_const
         xm = row_max4(sm, e, xm);
         if (e.cgp == 0) ws.EXMAX[(int64_t)l * ws.tiles * TILE + tile * TILE + e.row] = xm;
         rinv = rnew;
-        if (l < 3) publish_a(sm);
+        if (l < 3) publish_a_from(sm, nch);
       }
     }
     epi_bar();
@@ -755,6 +763,7 @@ __device__ __forceinline__ float actor_fwd_layer(SM& sm, Epi& e, float us, const
     for (int i = 0; i < 16; ++i) h[i] = leaky(fmaf(v[i], us, __ldg(bias + 16 * ch + i)));
     ws_store16(Hp, ACTOR_H, tile, 16 * ch, e.row, h);
     put_a16(sm, e, 16 * ch, h, s);
+    publish_a_group(sm, ch >> 2);                 // 256 columns = all A_GROUPS groups, one per iteration
   }
   return rnew;
 }
@@ -778,11 +787,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_actor_fwd(const __grid_consta
       float rinv = state_prologue(sm, e, P, state, b, valid, ws.XNA, tile, ws.amax + AM_XNA);
       publish_a(sm);
       wait_acc(sm, e);
-      rinv = actor_fwd_layer(sm, e, rinv * US[0], actor + AL.b1, ws.H1, tile, ws.amax + AM_H1);
-      publish_a(sm);
+      rinv = actor_fwd_layer(sm, e, rinv * US[0], actor + AL.b1, ws.H1, tile, ws.amax + AM_H1);      // (publishes the next A image group by group)
       wait_acc(sm, e);
       rinv = actor_fwd_layer(sm, e, rinv * US[1], actor + AL.b2, ws.H2, tile, ws.amax + AM_H2);
-      publish_a(sm);
       wait_acc(sm, e);
       if (e.cgp == 0) {
         float a[16];
@@ -906,11 +913,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_actor_bwd(const __grid_consta
           }
           ws_store16(Ep, ACTOR_H, tile, 16 * ch, e.row, v);
           warp_colsum16(sm.colsum, l * ACTOR_H + 16 * ch, v, e.lane);        // d b2 | d b1
-          if (l == 0) put_a16(sm, e, 16 * ch, v, s);
+          if (l == 0) {
+            put_a16(sm, e, 16 * ch, v, s);
+            publish_a_group(sm, j);
+          }
         }
         amax_update(ws.amax + (l == 0 ? AM_E2 : AM_E1), mx, e.lane);
         rinv = rnew;
-        if (l == 0) publish_a(sm);
       }
     }
     epi_bar();
@@ -1178,13 +1187,13 @@ __global__ void __launch_bounds__(256) k_tc_wgrad_reduce(const WgTable T, const 
   const bool live = idx < J.M * n4;
   const int cg = live ? idx / J.M : 0, m = live ? idx - cg * J.M : 0, c = 4 * cg;
   const int c0 = T.cta0[blockIdx.y], nct = T.cta0[blockIdx.y + 1] - c0;
-  const int64_t units = ws.tiles * (TILE / WG_KS);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live && c < J.N_real) {
 #pragma unroll 4
+    // (every CTA of a job wrote its block: wg_assign never gives a job more CTAs than it has units.  An earlier version re-derived
+    //  "did CTA ci get a unit" here with two 64-bit divisions per slice -- ncu: 18 us for the actor's reduce, all of it integer division)
     for (int ci = part; ci < nct; ci += WGR_LANES) {
-      const bool wrote = units * ci / nct != units * (ci + 1) / nct;        // a CTA without units wrote nothing
-      const float4 p = wrote ? __ldg(reinterpret_cast<const float4*>(ws.PART + (int64_t)(c0 + ci) * TILE * 256) + cg * TILE + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 p = __ldg(reinterpret_cast<const float4*>(ws.PART + (int64_t)(c0 + ci) * TILE * 256) + cg * TILE + m);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
   }
@@ -1316,7 +1325,7 @@ static void wg_assign(WgTable& T, int ctas, int64_t tiles) {
   }
   T.cta0[0] = 0;
   for (int j = 0; j < T.njobs; ++j) {
-    const int64_t per = (int64_t)(hi / unit_cost[j]);
+    const int64_t per = (int64_t)(hi / unit_cost[j]);          // >= 1: a job never gets more CTAs than units, every CTA writes its block
     T.cta0[j + 1] = T.cta0[j] + (int)((units + per - 1) / per);
   }
 }
