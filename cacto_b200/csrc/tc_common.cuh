@@ -153,16 +153,26 @@ __host__ __device__ __forceinline__ float pow2_scale(float m, float& inv) {
 // instead the dropped a_lo w_lo term of the split product is 4 x larger (2^-20 instead of 2^-22 relative)
 __device__ __forceinline__ float hi11(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
-// hi / lo fp16 split of 8 scaled values -> one 16-byte unit of each image (hi: 11 significant bits, exact in fp16; lo = x - hi rounded)
+// hi / lo fp16 split of a scaled pair: hi = RN_fp16(a) (11 significant bits), lo = RN_fp16(a - hi) -- the subtraction is exact in
+// fp32.  Packed fp32x2 multiply / subtract and the f16x2 conversions: 6 instructions per pair (the integer rounding trick of hi11
+// plus scalar arithmetic took 10; the chunk passes of the chain kernels are issue-bound).
+__device__ __forceinline__ void split_pair(float x0, float x1, float scale, uint32_t& h, uint32_t& l) {
+  uint64_t a, d;
+  asm("{\n\t.reg .b64 x, s;\n\tmov.b64 x, {%1, %2};\n\tmov.b64 s, {%3, %3};\n\tmul.rn.f32x2 %0, x, s;\n\t}" : "=l"(a) : "f"(x0), "f"(x1), "f"(scale));
+  float a0, a1, h0, h1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+  h = pack_h2(a0, a1);
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(h0), "=f"(h1) : "r"(h));
+  asm("{\n\t.reg .b64 hh, m1;\n\tmov.b64 hh, {%2, %3};\n\tmov.b64 m1, {%4, %4};\n\tfma.rn.f32x2 %0, hh, m1, %1;\n\t}" : "=l"(d) : "l"(a), "f"(h0), "f"(h1), "f"(-1.f));
+  float d0, d1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+  l = pack_h2(d0, d1);
+}
+// ... of 8 scaled values -> one 16-byte unit of each image
 __device__ __forceinline__ void split8(const float* x, float scale, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const float a0 = x[2 * p] * scale, a1 = x[2 * p + 1] * scale;
-    const float h0 = hi11(a0), h1 = hi11(a1);
-    h[p] = pack_h2(h0, h1);
-    l[p] = pack_h2(a0 - h0, a1 - h1);
-  }
+  for (int p = 0; p < 4; ++p) split_pair(x[2 * p], x[2 * p + 1], scale, h[p], l[p]);
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }

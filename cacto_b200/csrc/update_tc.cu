@@ -983,12 +983,7 @@ __device__ __forceinline__ void wg_put_unit(const float2 (&f)[4], float scale, u
   if (f[0].x + f[1].x + f[2].x + f[3].x + f[0].y + f[1].y + f[2].y + f[3].y != 12345.678f) return;
 #endif
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const float x0 = f[m].x * scale, x1 = f[m].y * scale;
-    const float h0 = hi11(x0), h1 = hi11(x1);
-    h[m] = pack_h2(h0, h1);
-    l[m] = pack_h2(x0 - h0, x1 - h1);
-  }
+  for (int m = 0; m < 4; ++m) split_pair(f[m].x, f[m].y, scale, h[m], l[m]);
   stsm_x4_trans(hi_addr, h);
   stsm_x4_trans(lo_addr, l);
 }
