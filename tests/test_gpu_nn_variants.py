@@ -66,7 +66,9 @@ def test_variant_update_step_matches_oracle(critic_type):
         for m, r in zip(rl.critic_model.get_weights() + rl.actor_model.get_weights(), critic + actor):
             assert rel(m, r) < 1e-4
         for m, r in zip(rl.target_critic.get_weights(), target):
-            assert rel(m, r) < 1e-5
+            # a zero-initialised bias of the target is tau x the critic's: it inherits the critic's relative error (an Adam step with
+            # |g| ~ eps is the sensitive case: the relu variant has such a bias, and fp32 atomics reorder from run to run)
+            assert rel(m, r) < 1e-4
     ug = rl.make_update_graph(64)
     for k_, t_ in zip(('state', 'state_next', 'partial_rtg', 'dVdx', 'done', 'term', 'weights'), (s, sn, pr, dv, d, term, w)):
         ug.io[k_].copy_(torch.as_tensor(t_))
