@@ -105,8 +105,11 @@ struct JointRot {
 
 // tau = M(q) a + nle(q, v) for an all-revolute chain (recursive Newton-Euler in link frames).
 // with_vel = false drops every velocity term (used for the columns of M).
+// sc_pre: optional [2 N] = sin q_0 .. sin q_{N-1}, cos q_0 .. (the UR5 step and derivative call this seven times at the same q:
+// the fp64 sincos of the six joints were 36 of the 42 evaluated per step).
 template <typename S, int N, bool WITH_VEL>
-__device__ void chain_rnea(const cacto_chain& ch, const S* q, const S* v, const S* a, typename scalar_of<S>::type grav, S* tau) {
+__device__ void chain_rnea(const cacto_chain& ch, const S* q, const S* v, const S* a, typename scalar_of<S>::type grav, S* tau,
+                           const S* sc_pre = nullptr) {
   typedef typename scalar_of<S>::type T;
   S sn[N], cs[N];
   S Fv[N][3], Nv[N][3];
@@ -117,7 +120,8 @@ __device__ void chain_rnea(const cacto_chain& ch, const S* q, const S* v, const 
     JointRot<S> J;
     for (int k = 0; k < 9; ++k) J.F[k] = T(ch.R[i][k]);
     J.axis = ch.axis[i];
-    sincos_(q[i], J.s, J.c);
+    if (sc_pre != nullptr) { J.s = sc_pre[i]; J.c = sc_pre[N + i]; }
+    else sincos_(q[i], J.s, J.c);
     sn[i] = J.s; cs[i] = J.c;
     S p[3] = {S(T(ch.p[i][0])), S(T(ch.p[i][1])), S(T(ch.p[i][2]))};
     S t0[3], t1[3], wp[3];
@@ -301,15 +305,84 @@ template <> struct SysDims<CACTO_UR5> { static constexpr int NX = 12, NA = 6; };
 
 // UR5 helpers: mass matrix (row-major 6x6) and nle.
 template <typename T>
-__device__ void ur5_mass_matrix(const cacto_chain& ch, const T* q, T* M) {
-  T z[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-  for (int j = 0; j < 6; ++j) {
-    T e[6] = {0, 0, 0, 0, 0, 0};
-    e[j] = T(1);
-    T col[6];
-    chain_rnea<T, 6, false>(ch, q, z, e, T(0), col);
-    for (int i = 0; i < 6; ++i) M[i * 6 + j] = col[i];
+__device__ __forceinline__ void ur5_sincos(const T* q, T* sc) {
+  for (int i = 0; i < 6; ++i) sincos_(q[i], sc[i], sc[6 + i]);
+}
+// Composite-rigid-body algorithm in link frames (3-vector form, same frame conventions as chain_rnea): composite inertias
+// (mass, first moment h = m c, rotational inertia about the frame origin) from the tip to the base, then for joint i the
+// wrench (n, f) = (I_i e_i, e_i x h_i) of a unit joint acceleration, carried down the chain: M[i][j] = e_j . n in frame j.
+// A third of the arithmetic of the six velocity-free RNEA passes it replaces (each of which re-derived every link's motion).
+template <typename T>
+__device__ void ur5_mass_matrix(const cacto_chain& ch, const T* q, T* M, const T* sc) {
+  (void)q;
+  T R[6][9];                      // R_i: frame i -> frame i - 1 (= Rfix_i Rot(axis_i, q_i))
+  T cm[6], chh[6][3], cI[6][6];   // composite mass, first moment, inertia (xx, yy, zz, xy, xz, yz) about the frame origin
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    JointRot<T> J;
+    for (int k = 0; k < 9; ++k) J.F[k] = T(ch.R[i][k]);
+    J.axis = ch.axis[i];
+    J.s = sc[i]; J.c = sc[6 + i];
+    for (int r = 0; r < 3; ++r) J.rot_axis_T(&J.F[3 * r], &R[i][3 * r]);          // row r of Rfix times Rot
+    const T m = T(ch.mass[i]), cx = T(ch.com[i][0]), cy = T(ch.com[i][1]), cz = T(ch.com[i][2]);
+    cm[i] = m;
+    chh[i][0] = m * cx; chh[i][1] = m * cy; chh[i][2] = m * cz;
+    cI[i][0] = T(ch.inertia[i][0]) + m * (cy * cy + cz * cz);
+    cI[i][1] = T(ch.inertia[i][1]) + m * (cx * cx + cz * cz);
+    cI[i][2] = T(ch.inertia[i][2]) + m * (cx * cx + cy * cy);
+    cI[i][3] = T(ch.inertia[i][3]) - m * cx * cy;
+    cI[i][4] = T(ch.inertia[i][4]) - m * cx * cz;
+    cI[i][5] = T(ch.inertia[i][5]) - m * cy * cz;
+  }
+#pragma unroll
+  for (int i = 5; i >= 1; --i) {  // composite of link i (frame i) added to link i - 1 (frame i - 1)
+    const T* Ri = R[i];
+    const T p0 = T(ch.p[i][0]), p1 = T(ch.p[i][1]), p2 = T(ch.p[i][2]), m = cm[i];
+    T h[3];
+    for (int r = 0; r < 3; ++r) h[r] = Ri[3 * r] * chh[i][0] + Ri[3 * r + 1] * chh[i][1] + Ri[3 * r + 2] * chh[i][2];
+    // A = I R^T (I symmetric), then Ir = R A
+    const T ixx = cI[i][0], iyy = cI[i][1], izz = cI[i][2], ixy = cI[i][3], ixz = cI[i][4], iyz = cI[i][5];
+    T A[3][3];
+    for (int c = 0; c < 3; ++c) {
+      A[0][c] = ixx * Ri[3 * c] + ixy * Ri[3 * c + 1] + ixz * Ri[3 * c + 2];
+      A[1][c] = ixy * Ri[3 * c] + iyy * Ri[3 * c + 1] + iyz * Ri[3 * c + 2];
+      A[2][c] = ixz * Ri[3 * c] + iyz * Ri[3 * c + 1] + izz * Ri[3 * c + 2];
+    }
+    auto rAr = [&](int r, int c) { return Ri[3 * r] * A[0][c] + Ri[3 * r + 1] * A[1][c] + Ri[3 * r + 2] * A[2][c]; };
+    const T pp = p0 * p0 + p1 * p1 + p2 * p2, ph = p0 * h[0] + p1 * h[1] + p2 * h[2];
+    const T dg = m * pp + T(2) * ph;                       // the isotropic part of the origin shift
+    cm[i - 1] += m;
+    chh[i - 1][0] += h[0] + m * p0; chh[i - 1][1] += h[1] + m * p1; chh[i - 1][2] += h[2] + m * p2;
+    cI[i - 1][0] += rAr(0, 0) + dg - m * p0 * p0 - T(2) * p0 * h[0];
+    cI[i - 1][1] += rAr(1, 1) + dg - m * p1 * p1 - T(2) * p1 * h[1];
+    cI[i - 1][2] += rAr(2, 2) + dg - m * p2 * p2 - T(2) * p2 * h[2];
+    cI[i - 1][3] += rAr(0, 1) - m * p0 * p1 - (p0 * h[1] + h[0] * p1);
+    cI[i - 1][4] += rAr(0, 2) - m * p0 * p2 - (p0 * h[2] + h[0] * p2);
+    cI[i - 1][5] += rAr(1, 2) - m * p1 * p2 - (p1 * h[2] + h[1] * p2);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int ax = ch.axis[i];
+    T n[3], f[3];
+    // n = I_i e, f = e x h_i
+    if (ax == 0) { n[0] = cI[i][0]; n[1] = cI[i][3]; n[2] = cI[i][4]; f[0] = T(0); f[1] = -chh[i][2]; f[2] = chh[i][1]; }
+    else if (ax == 1) { n[0] = cI[i][3]; n[1] = cI[i][1]; n[2] = cI[i][5]; f[0] = chh[i][2]; f[1] = T(0); f[2] = -chh[i][0]; }
+    else { n[0] = cI[i][4]; n[1] = cI[i][5]; n[2] = cI[i][2]; f[0] = -chh[i][1]; f[1] = chh[i][0]; f[2] = T(0); }
+    M[i * 6 + i] = axis_get(n, ax);
+#pragma unroll
+    for (int j = i; j >= 1; --j) {                         // (n, f) from frame j to frame j - 1
+      const T* Rj = R[j];
+      T fp[3], np[3], pj[3] = {T(ch.p[j][0]), T(ch.p[j][1]), T(ch.p[j][2])}, t[3];
+      for (int r = 0; r < 3; ++r) {
+        fp[r] = Rj[3 * r] * f[0] + Rj[3 * r + 1] * f[1] + Rj[3 * r + 2] * f[2];
+        np[r] = Rj[3 * r] * n[0] + Rj[3 * r + 1] * n[1] + Rj[3 * r + 2] * n[2];
+      }
+      cross3(pj, fp, t);
+      for (int r = 0; r < 3; ++r) { f[r] = fp[r]; n[r] = np[r] + t[r]; }
+      const T mij = axis_get(n, (int)ch.axis[j - 1]);
+      M[i * 6 + (j - 1)] = mij;
+      M[(j - 1) * 6 + i] = mij;
+    }
   }
 }
 
@@ -352,9 +425,10 @@ __device__ __forceinline__ void sys_step(const cacto_sys_params& P, const T* x, 
       xn[3 + k] = x[3 + k] + st.acc[k] * dt;
     }
   } else {
-    T M[36], rhs[6], z[6] = {0, 0, 0, 0, 0, 0};
-    ur5_mass_matrix<T>(P.chain, x, M);
-    chain_rnea<T, 6, true>(P.chain, x, x + 6, z, T(P.chain.gravity), rhs);
+    T M[36], rhs[6], z[6] = {0, 0, 0, 0, 0, 0}, sc[12];
+    ur5_sincos<T>(x, sc);
+    ur5_mass_matrix<T>(P.chain, x, M, sc);
+    chain_rnea<T, 6, true>(P.chain, x, x + 6, z, T(P.chain.gravity), rhs, sc);
     for (int k = 0; k < 6; ++k) rhs[k] = u[k] - rhs[k];
     chol_factor<T, 6>(M);
     chol_solve<T, 6>(M, rhs);
@@ -393,8 +467,9 @@ __device__ __forceinline__ void sys_Fu(const cacto_sys_params& P, const T* x, T*
     const int ix[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Fu[(3 + i) * NA + j] = dt * Mi[ix[i][j]];
   } else {
-    T M[36];
-    ur5_mass_matrix<T>(P.chain, x, M);
+    T M[36], sc[12];
+    ur5_sincos<T>(x, sc);
+    ur5_mass_matrix<T>(P.chain, x, M, sc);
     chol_factor<T, 6>(M);
 #pragma unroll 1
     for (int j = 0; j < 6; ++j) {
@@ -488,10 +563,11 @@ __device__ __forceinline__ void sys_jac(const cacto_sys_params& P, const T* x, c
   } else {
     // UR5: a from the real pass, then tangent-mode RNEA at fixed a for d tau/dq_j and d tau/dv_j:
     // da/dz = -Minv d tau/dz.
-    T L[36], acc[6], z[6] = {0, 0, 0, 0, 0, 0};
+    T L[36], acc[6], z[6] = {0, 0, 0, 0, 0, 0}, sc[12];
     const T g = T(P.chain.gravity);
-    ur5_mass_matrix<T>(P.chain, x, L);
-    chain_rnea<T, 6, true>(P.chain, x, x + 6, z, g, acc);
+    ur5_sincos<T>(x, sc);
+    ur5_mass_matrix<T>(P.chain, x, L, sc);
+    chain_rnea<T, 6, true>(P.chain, x, x + 6, z, g, acc, sc);
     for (int k = 0; k < 6; ++k) acc[k] = u[k] - acc[k];
     chol_factor<T, 6>(L);
     chol_solve<T, 6>(L, acc);
@@ -502,7 +578,9 @@ __device__ __forceinline__ void sys_jac(const cacto_sys_params& P, const T* x, c
       D qd[6], vd[6], ad[6], td[6];
       for (int k = 0; k < 6; ++k) { qd[k] = D(x[k]); vd[k] = D(x[6 + k]); ad[k] = D(acc[k]); }
       if (j < 6) qd[j].d = T(1); else vd[j - 6].d = T(1);
-      chain_rnea<D, 6, true>(P.chain, qd, vd, ad, g, td);
+      D scd[12];                                   // sin / cos of the dual angles from the real ones: (s, c dq), (c, -s dq)
+      for (int k = 0; k < 6; ++k) { scd[k] = D(sc[k], sc[6 + k] * qd[k].d); scd[6 + k] = D(sc[6 + k], -sc[k] * qd[k].d); }
+      chain_rnea<D, 6, true>(P.chain, qd, vd, ad, g, td, scd);
       T col[6];
       for (int k = 0; k < 6; ++k) col[k] = td[k].d;
       chol_solve<T, 6>(L, col);
