@@ -481,6 +481,38 @@ __device__ __forceinline__ void sys_Fu(const cacto_sys_params& P, const T* x, T*
   }
 }
 
+// x' and Fu at the same (x, u) -- what the actor update needs per sample (NeuralNetwork.py:185-197).  For the UR5 both come from ONE
+// mass matrix and ONE Cholesky factor (calling sys_step and sys_Fu rebuilt and refactored M); identical values either way.
+template <int SYS, typename T>
+__device__ __forceinline__ void sys_step_Fu(const cacto_sys_params& P, const T* x, const T* u, T* xn, T* Fu) {
+  if (SYS != CACTO_UR5) {
+    sys_step<SYS, T>(P, x, u, xn);
+    sys_Fu<SYS, T>(P, x, Fu);
+  } else {
+    constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA;
+    const T dt = T(P.dt);
+    T M[36], rhs[6], z[6] = {0, 0, 0, 0, 0, 0}, sc[12];
+    ur5_sincos<T>(x, sc);
+    ur5_mass_matrix<T>(P.chain, x, M, sc);
+    chain_rnea<T, 6, true>(P.chain, x, x + 6, z, T(P.chain.gravity), rhs, sc);
+    for (int k = 0; k < 6; ++k) rhs[k] = u[k] - rhs[k];
+    chol_factor<T, 6>(M);
+    chol_solve<T, 6>(M, rhs);
+    for (int k = 0; k < 6; ++k) {
+      xn[k] = x[k] + x[6 + k] * dt;
+      xn[6 + k] = x[6 + k] + rhs[k] * dt;
+    }
+    for (int k = 0; k < NX * NA; ++k) Fu[k] = T(0);
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) {
+      T e[6] = {0, 0, 0, 0, 0, 0};
+      e[j] = T(1);
+      chol_solve<T, 6>(M, e);
+      for (int i = 0; i < 6; ++i) Fu[(6 + i) * NA + j] = dt * e[i];
+    }
+  }
+}
+
 // Discrete-time Jacobians Fx (NX x NX), Fu (NX x NA).  environment.py:111-132,:221-233,:420-435,:567-582.
 template <int SYS, typename T>
 __device__ __forceinline__ void sys_jac(const cacto_sys_params& P, const T* x, const T* u, T* Fx, T* Fu) {

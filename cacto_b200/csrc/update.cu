@@ -521,9 +521,8 @@ __global__ void __launch_bounds__(UP_NT) k_actor_grad(const __grid_constant__ ca
         u[j] = (double)sm.ACT[tid][j];
         if (actions_out != nullptr) actions_out[b * NA + j] = sm.ACT[tid][j];
       }
-      sys_step<SYS, double>(P, x, u, xn);
+      sys_step_Fu<SYS, double>(P, x, u, xn, Fu);
       xn[NX] = x[NX] + P.dt;
-      sys_Fu<SYS, double>(P, x, Fu);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         const double inv = P.normalize ? 1.0 / P.state_norm[i] : 1.0;

@@ -835,9 +835,8 @@ __global__ void __launch_bounds__(128) k_tc_actor_env(const __grid_constant__ ca
     uf[j] = ws.ACT[b * NA + j];
     u[j] = (double)uf[j];
   }
-  sys_step<SYS, double>(P, x, u, xn);
+  sys_step_Fu<SYS, double>(P, x, u, xn, Fu);
   xn[NX] = x[NX] + P.dt;
-  sys_Fu<SYS, double>(P, x, Fu);
 #pragma unroll
   for (int j = 0; j < NS; ++j) ws.SP[b * NS + j] = (float)xn[j];
 #pragma unroll
