@@ -485,7 +485,20 @@ __device__ __forceinline__ void sys_Fu(const cacto_sys_params& P, const T* x, T*
 // mass matrix and ONE Cholesky factor (calling sys_step and sys_Fu rebuilt and refactored M); identical values either way.
 template <int SYS, typename T>
 __device__ __forceinline__ void sys_step_Fu(const cacto_sys_params& P, const T* x, const T* u, T* xn, T* Fu) {
-  if (SYS != CACTO_UR5) {
+  if (SYS == CACTO_MANIPULATOR) {                          // the forward dynamics already hold Minv (and the two sincos)
+    constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA;
+    const T dt = T(P.dt);
+    Planar3R<T> R(P.chain);
+    Planar3RState<T> st;
+    planar3r_forward(R, x, x + 3, u, st);
+    for (int k = 0; k < 3; ++k) {
+      xn[k] = x[k] + x[3 + k] * dt;
+      xn[3 + k] = x[3 + k] + st.acc[k] * dt;
+    }
+    for (int k = 0; k < NX * NA; ++k) Fu[k] = T(0);
+    const int ix[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Fu[(3 + i) * NA + j] = dt * st.Mi[ix[i][j]];
+  } else if (SYS != CACTO_UR5) {
     sys_step<SYS, T>(P, x, u, xn);
     sys_Fu<SYS, T>(P, x, Fu);
   } else {
