@@ -54,6 +54,10 @@ template <typename T> __device__ __forceinline__ HDual<T> log_(HDual<T> x) {
   const T r = T(1) / x.v;
   return hd_chain(x, log_(x.v), r, -r * r);
 }
+template <typename T> __device__ __forceinline__ void sincos_from(HDual<T> x, T sv, T cv, HDual<T>& s, HDual<T>& c) {
+  s = hd_chain(x, sv, cv, -sv);
+  c = hd_chain(x, cv, -sv, -cv);
+}
 template <typename T> __device__ __forceinline__ void sincos_(HDual<T> x, HDual<T>& s, HDual<T>& c) {
   T sv, cv;
   sincos_(x.v, sv, cv);
@@ -87,13 +91,15 @@ __global__ void __launch_bounds__(128) k_bp_knots(const __grid_constant__ cacto_
   double* o = ws + k * W;
   double* lx = o, *lxx = o + NX, *A = lxx + NX * NX, *Bm = A + NX * NX, *lu = Bm + NX * NA, *luu = lu + NA;
   const double* w = last ? P.w_terminal : P.w_running;
-  // l_x, l_xx: one hyper-dual evaluation of the reward per pair (i <= j)
+  // l_x, l_xx: one hyper-dual evaluation of the reward per pair (i <= j); the UR5's joint sin / cos once per knot, not per pair
+  double sc_real[12];
+  if constexpr (SYS == CACTO_UR5) ur5_sincos<double>(x, sc_real);
   for (int i = 0; i < NX; ++i) {
     for (int j = i; j < NX; ++j) {
       HDual<double> xs[NX + 1];
 #pragma unroll
       for (int c = 0; c <= NX; ++c) xs[c] = HDual<double>(x[c], c == i ? 1.0 : 0.0, c == j ? 1.0 : 0.0, 0.0);
-      const HDual<double> r = sys_reward<SYS, HDual<double>>(P, w, xs, (const HDual<double>*)nullptr, false);
+      const HDual<double> r = sys_reward<SYS, HDual<double>>(P, w, xs, (const HDual<double>*)nullptr, false, SYS == CACTO_UR5 ? sc_real : nullptr);
       lxx[i * NX + j] = r.ab;
       lxx[j * NX + i] = r.ab;
       if (j == i) lx[i] = r.a;
@@ -115,9 +121,10 @@ __global__ void __launch_bounds__(128) k_bp_knots(const __grid_constant__ cacto_
 }
 
 // ------------------------------------------------------------------------------------------ pinv of a small symmetric matrix
+// Cyclic Jacobi on shared-memory arrays A, V (M x M each), executed by ONE lane (the rotations are sequential); the caller
+// synchronises the warp around it.  Same arithmetic and rotation order as the first version, which kept A and V in local memory.
 template <int M>
-__device__ void pinv_sym(const double* Q, double* Pinv) {
-  double A[M * M], V[M * M];
+__device__ void pinv_sym_lane(const double* Q, double* A, double* V) {
   for (int i = 0; i < M; ++i)
     for (int j = 0; j < M; ++j) {
       A[i * M + j] = 0.5 * (Q[i * M + j] + Q[j * M + i]);
@@ -129,7 +136,9 @@ __device__ void pinv_sym(const double* Q, double* Pinv) {
       for (int j = 0; j < M; ++j) {
         if (i != j) off += A[i * M + j] * A[i * M + j]; else diag += A[i * M + j] * A[i * M + j];
       }
-    if (off <= 1e-40 * diag || off == 0.0) break;
+    // converged once the off-diagonal mass is at rounding level (sums of SQUARES: 1e-30 = (1e-15)^2).  The first version asked for
+    // 1e-40, which rounding never reaches: all 40 sweeps ran at every knot -- 180 k warp instructions per knot for the UR5 (ncu).
+    if (off <= 1e-30 * diag || off == 0.0) break;
     for (int p = 0; p < M - 1; ++p)
       for (int q = p + 1; q < M; ++q) {
         const double apq = A[p * M + q];
@@ -154,103 +163,128 @@ __device__ void pinv_sym(const double* Q, double* Pinv) {
         }
       }
   }
-  double lmax = 0.0;
-  for (int i = 0; i < M; ++i) lmax = fmax(lmax, fabs(A[i * M + i]));
-  const double cut = 1e-15 * lmax;
-  for (int i = 0; i < M * M; ++i) Pinv[i] = 0.0;
-  for (int e = 0; e < M; ++e) {
-    const double l = A[e * M + e];
-    if (fabs(l) <= cut) continue;
-    const double inv = 1.0 / l;
-    for (int i = 0; i < M; ++i)
-      for (int j = 0; j < M; ++j) Pinv[i * M + j] += inv * V[i * M + e] * V[j * M + e];
-  }
 }
 
 // ------------------------------------------------------------------------------------------ value recursion
+// One WARP per trajectory, all matrices in shared memory: every entry of V_xx A, V_xx B, the Q blocks, the gains and the new
+// V_x / V_xx is a short dot product owned by one lane (entries are dealt round-robin), a __syncwarp() between the stages.
+// (First version: one THREAD per trajectory with the same loops over local-memory arrays -- 0.58 ms per knot for the UR5's 12 x 12
+// blocks, every operand an L1 round trip on a dependent chain; each entry is computed by the same expression as before.)
 template <int SYS>
 __global__ void __launch_bounds__(32) k_bp_riccati(const int64_t* __restrict__ offsets, int E, const double* __restrict__ ws, double mu,
                                                    double* __restrict__ Vx_out) {
   constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA, W = bp_stride(NX, NA);
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double Vx[NX], Vxx[NX * NX], VA[NX * NX], VB[NX * NA], Qx[NX], Qu[NA], Qxx[NX * NX], Quu[NA * NA], Qxu[NX * NA];
+  __shared__ double Pi[NA * NA], PQu[NA], G[NX * NA], JA[NA * NA], JV[NA * NA], knot[W];
+  const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= E) return;
   const int64_t k0 = offsets[e], k1 = offsets[e + 1];
   if (k1 <= k0) return;
-  double Vx[NX], Vxx[NX * NX];
   {
     const double* o = ws + (k1 - 1) * W;                          // terminal knot: V = l (TO.py:172-174)
-    for (int i = 0; i < NX; ++i) Vx[i] = o[i];
-    for (int i = 0; i < NX * NX; ++i) Vxx[i] = o[NX + i];
-    for (int i = 0; i < NX; ++i) Vx_out[(k1 - 1) * (NX + 1) + i] = Vx[i];
-    Vx_out[(k1 - 1) * (NX + 1) + NX] = 0.0;
+    for (int i = lane; i < NX; i += 32) { Vx[i] = o[i]; Vx_out[(k1 - 1) * (NX + 1) + i] = o[i]; }
+    for (int i = lane; i < NX * NX; i += 32) Vxx[i] = o[NX + i];
+    if (lane == 0) Vx_out[(k1 - 1) * (NX + 1) + NX] = 0.0;
   }
+  __syncwarp();
   for (int64_t k = k1 - 2; k >= k0; --k) {
-    const double* o = ws + k * W;
-    const double* lx = o, *lxx = o + NX, *A = lxx + NX * NX, *Bm = A + NX * NX, *lu = Bm + NX * NA, *luu = lu + NA;
-    double VA[NX * NX], VB[NX * NA];                               // V_xx A, V_xx B
-    for (int i = 0; i < NX; ++i) {
-      for (int j = 0; j < NX; ++j) {
-        double s = 0.0;
+    for (int i = lane; i < W; i += 32) knot[i] = ws[k * W + i];
+    __syncwarp();
+    const double* lx = knot, *lxx = knot + NX, *A = lxx + NX * NX, *Bm = A + NX * NX, *lu = Bm + NX * NA, *luu = lu + NA;
+    for (int idx = lane; idx < NX * (NX + NA); idx += 32) {       // V_xx A | V_xx B
+      const int i = idx / (NX + NA), j = idx - i * (NX + NA);
+      double s = 0.0;
+      if (j < NX) {
         for (int c = 0; c < NX; ++c) s += Vxx[i * NX + c] * A[c * NX + j];
         VA[i * NX + j] = s;
+      } else {
+        for (int c = 0; c < NX; ++c) s += Vxx[i * NX + c] * Bm[c * NA + (j - NX)];
+        VB[i * NA + (j - NX)] = s;
       }
-      for (int j = 0; j < NA; ++j) {
+    }
+    __syncwarp();
+    for (int idx = lane; idx < (NX + NA) * (1 + NX + NA); idx += 32) {   // Q_x | Q_xx | Q_xu ; Q_u | Q_uu (rows of [A B]^T)
+      const int r = idx / (1 + NX + NA), cidx = idx - r * (1 + NX + NA);
+      if (r < NX) {
+        const int i = r;
+        if (cidx == 0) {
+          double s = lx[i];
+          for (int c = 0; c < NX; ++c) s += A[c * NX + i] * Vx[c];
+          Qx[i] = s;
+        } else if (cidx <= NX) {
+          const int j = cidx - 1;
+          double t = lxx[i * NX + j];
+          for (int c = 0; c < NX; ++c) t += A[c * NX + i] * VA[c * NX + j];
+          Qxx[i * NX + j] = t;
+        } else {
+          const int j = cidx - 1 - NX;
+          double t = 0.0;                                          // l_xu = 0: the cost is separable in x and u
+          for (int c = 0; c < NX; ++c) t += A[c * NX + i] * VB[c * NA + j];
+          Qxu[i * NA + j] = t;
+        }
+      } else {
+        const int i = r - NX;
+        if (cidx == 0) {
+          double s = lu[i];
+          for (int c = 0; c < NX; ++c) s += Bm[c * NA + i] * Vx[c];
+          Qu[i] = s;
+        } else if (cidx <= NA) {
+          const int j = cidx - 1;
+          double t = (i == j) ? luu[i] + mu : 0.0;                 // Qbar_uu = Q_uu + mu I (TO.py:192)
+          for (int c = 0; c < NX; ++c) t += Bm[c * NA + i] * VB[c * NA + j];
+          Quu[i * NA + j] = t;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) pinv_sym_lane<NA>(Quu, JA, JV);                 // eigen-decomposition of Qbar_uu
+    __syncwarp();
+    {
+      double lmax = 0.0;
+      for (int i = 0; i < NA; ++i) lmax = fmax(lmax, fabs(JA[i * NA + i]));
+      const double cut = 1e-15 * lmax;
+      for (int idx = lane; idx < NA * NA; idx += 32) {
+        const int i = idx / NA, j = idx - i * NA;
+        double acc = 0.0;
+        for (int ev = 0; ev < NA; ++ev) {
+          const double l = JA[ev * NA + ev];
+          if (fabs(l) <= cut) continue;
+          const double inv = 1.0 / l;
+          acc += inv * JV[i * NA + ev] * JV[j * NA + ev];
+        }
+        Pi[idx] = acc;
+      }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < NA + NX * NA; idx += 32) {          // pinv Q_u | Q_xu pinv
+      if (idx < NA) {
         double s = 0.0;
-        for (int c = 0; c < NX; ++c) s += Vxx[i * NX + c] * Bm[c * NA + j];
-        VB[i * NA + j] = s;
-      }
-    }
-    double Qx[NX], Qu[NA], Qxx[NX * NX], Quu[NA * NA], Qxu[NX * NA];
-    for (int i = 0; i < NX; ++i) {
-      double s = lx[i];
-      for (int c = 0; c < NX; ++c) s += A[c * NX + i] * Vx[c];
-      Qx[i] = s;
-      for (int j = 0; j < NX; ++j) {
-        double t = lxx[i * NX + j];
-        for (int c = 0; c < NX; ++c) t += A[c * NX + i] * VA[c * NX + j];
-        Qxx[i * NX + j] = t;
-      }
-      for (int j = 0; j < NA; ++j) {
-        double t = 0.0;                                            // l_xu = 0: the cost is separable in x and u
-        for (int c = 0; c < NX; ++c) t += A[c * NX + i] * VB[c * NA + j];
-        Qxu[i * NA + j] = t;
-      }
-    }
-    for (int i = 0; i < NA; ++i) {
-      double s = lu[i];
-      for (int c = 0; c < NX; ++c) s += Bm[c * NA + i] * Vx[c];
-      Qu[i] = s;
-      for (int j = 0; j < NA; ++j) {
-        double t = (i == j) ? luu[i] + mu : 0.0;                   // Qbar_uu = Q_uu + mu I (TO.py:192)
-        for (int c = 0; c < NX; ++c) t += Bm[c * NA + i] * VB[c * NA + j];
-        Quu[i * NA + j] = t;
-      }
-    }
-    double Pi[NA * NA], PQu[NA], G[NX * NA];                       // pinv, pinv Q_u, Q_xu pinv
-    pinv_sym<NA>(Quu, Pi);
-    for (int i = 0; i < NA; ++i) {
-      double s = 0.0;
-      for (int j = 0; j < NA; ++j) s += Pi[i * NA + j] * Qu[j];
-      PQu[i] = s;
-    }
-    for (int i = 0; i < NX; ++i)
-      for (int j = 0; j < NA; ++j) {
+        for (int j = 0; j < NA; ++j) s += Pi[idx * NA + j] * Qu[j];
+        PQu[idx] = s;
+      } else {
+        const int i = (idx - NA) / NA, j = (idx - NA) - i * NA;
         double s = 0.0;
         for (int c = 0; c < NA; ++c) s += Qxu[i * NA + c] * Pi[c * NA + j];
         G[i * NA + j] = s;
       }
-    for (int i = 0; i < NX; ++i) {
-      double s = Qx[i];
-      for (int j = 0; j < NA; ++j) s -= Qxu[i * NA + j] * PQu[j];
-      Vx[i] = s;
-      for (int j = 0; j < NX; ++j) {
+    }
+    __syncwarp();
+    for (int idx = lane; idx < NX * (1 + NX); idx += 32) {         // V_x | V_xx
+      const int i = idx / (1 + NX), cidx = idx - i * (1 + NX);
+      if (cidx == 0) {
+        double s = Qx[i];
+        for (int j = 0; j < NA; ++j) s -= Qxu[i * NA + j] * PQu[j];
+        Vx[i] = s;
+        Vx_out[k * (NX + 1) + i] = s;
+      } else {
+        const int j = cidx - 1;
         double t = Qxx[i * NX + j];
         for (int c = 0; c < NA; ++c) t -= G[i * NA + c] * Qxu[j * NA + c];
         Vxx[i * NX + j] = t;
       }
     }
-    for (int i = 0; i < NX; ++i) Vx_out[k * (NX + 1) + i] = Vx[i];
-    Vx_out[k * (NX + 1) + NX] = 0.0;
+    if (lane == 0) Vx_out[k * (NX + 1) + NX] = 0.0;
+    __syncwarp();
   }
 }
 
@@ -259,7 +293,7 @@ static int launch_backward(const cacto_sys_params& P, const int64_t* offsets, in
                            double* ws, double* Vx, int64_t K, cudaStream_t st) {
   k_bp_knots<SYS><<<(unsigned)((K + 127) / 128), 128, 0, st>>>(P, offsets, E, states, controls, ws, K);
   CACTO_LAUNCH_CHECK();
-  k_bp_riccati<SYS><<<(unsigned)((E + 31) / 32), 32, 0, st>>>(offsets, E, ws, mu, Vx);
+  k_bp_riccati<SYS><<<(unsigned)E, 32, 0, st>>>(offsets, E, ws, mu, Vx);
   CACTO_LAUNCH_CHECK();
   return 0;
 }

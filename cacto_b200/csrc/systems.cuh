@@ -56,6 +56,13 @@ template <typename T> __device__ __forceinline__ void sincos_(Dual<T> x, Dual<T>
   s = Dual<T>(sv, cv * x.d);
   c = Dual<T>(cv, -sv * x.d);
 }
+// sin / cos of x given sin / cos of its real part (one overload per number type; HDual: backward.cu)
+__device__ __forceinline__ void sincos_from(float, float sv, float cv, float& s, float& c) { s = sv; c = cv; }
+__device__ __forceinline__ void sincos_from(double, double sv, double cv, double& s, double& c) { s = sv; c = cv; }
+template <typename T> __device__ __forceinline__ void sincos_from(Dual<T> x, T sv, T cv, Dual<T>& s, Dual<T>& c) {
+  s = Dual<T>(sv, cv * x.d);
+  c = Dual<T>(cv, -sv * x.d);
+}
 template <typename S> struct scalar_of { typedef S type; };
 template <typename T> struct scalar_of<Dual<T>> { typedef T type; };
 
@@ -643,8 +650,10 @@ __device__ __forceinline__ void sys_jac(const cacto_sys_params& P, const T* x, c
 }
 
 // End-effector position.  environment.py:146-156 (Pinocchio frame 'EE'), :245-250, :450-455, :597-602.
+// sc_real (UR5 only, optional): sin q_0 .. sin q_5, cos q_0 .. cos q_5 of the REAL joint angles, for callers that evaluate the
+// same configuration many times with different dual parts (the 78 hyper-dual reward evaluations per knot of the TO backward pass).
 template <int SYS, typename T>
-__device__ __forceinline__ void sys_ee(const cacto_sys_params& P, const T* x, T* p) {
+__device__ __forceinline__ void sys_ee(const cacto_sys_params& P, const T* x, T* p, const typename scalar_of<T>::type* sc_real = nullptr) {
   if (SYS == CACTO_SINGLE_INTEGRATOR || SYS == CACTO_CAR) {
     p[0] = x[0]; p[1] = x[1]; p[2] = T(0);
   } else if (SYS == CACTO_DOUBLE_INTEGRATOR) {
@@ -674,7 +683,8 @@ __device__ __forceinline__ void sys_ee(const cacto_sys_params& P, const T* x, T*
       JointRot<T> J;
       for (int k = 0; k < 9; ++k) J.F[k] = typename scalar_of<T>::type(P.chain.R[i][k]);
       J.axis = P.chain.axis[i];
-      sincos_(x[i], J.s, J.c);
+      if (sc_real != nullptr) sincos_from(x[i], sc_real[i], sc_real[6 + i], J.s, J.c);
+      else sincos_(x[i], J.s, J.c);
       T t[3];
       J.apply(v, t);
       for (int k = 0; k < 3; ++k) v[k] = t[k] + T(P.chain.p[i][k]);
@@ -697,10 +707,11 @@ __device__ __forceinline__ T park_obs(T x, T y, T xc, T yc, T Wx, T Wy, T k) {
 // Reward r(w, s, a).  environment.py:252-275 (SI), :329-351 (DI), :457-480 (car), :615-641 (car_park),
 // :695-723 (manipulator), :780-805 (UR5); bound_control_cost :158-163.  `u` may be nullptr.
 template <int SYS, typename T>
-__device__ __forceinline__ T sys_reward(const cacto_sys_params& P, const double* w, const T* x, const T* u, bool plain_ucost) {
+__device__ __forceinline__ T sys_reward(const cacto_sys_params& P, const double* w, const T* x, const T* u, bool plain_ucost,
+                                        const typename scalar_of<T>::type* sc_real = nullptr) {
   constexpr int NX = SysDims<SYS>::NX, NA = SysDims<SYS>::NA;
   T p[3];
-  sys_ee<SYS, T>(P, x, p);
+  sys_ee<SYS, T>(P, x, p, sc_real);
   const T alpha = T(P.alpha), alpha2 = T(P.alpha2);
   constexpr int DIMS = (SYS == CACTO_UR5) ? 3 : 2;
   T pk = T(0), dist = T(0);
