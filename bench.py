@@ -600,7 +600,8 @@ def run_b200(args):
                                 'backward pass; UNPINNED for pinocchio-backed dynamics and tensorflow update semantics (absent here): '
                                 'tests/golden/make_golden_ext.py is the kit that pins them where the wheels exist',
                       'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s,
-                      'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world, 'update_kernels_per_update': 6,
+                      'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world, 'update_kernels_per_update': 5,      # schedules (one launch for both optimizers), critic gradient, Adam + Polyak, actor gradient, Adam
+                      
                       'update_gradient_exchange': ('none (1 GPU)' if world == 1 else
                                                    'NVLink peer-memory sum inside the Adam kernels (k_adam_peer)' if rl._peer is not None else
                                                    'NCCL all-reduce per network'),
