@@ -468,6 +468,11 @@ def run_b200(args):
                 except Exception:
                     ug_ = None
             r_.peer_barrier()
+            # every update's loss is read back; the read of update k is issued behind it (asynchronous copy into pinned memory)
+            # and waited for after update k + 1 has been launched, so that the host's sampling work overlaps the device's update
+            loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+            loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            loss_host, n_read = float('nan'), 0
             for it in range(3 + e2e_updates):
                 if it == 3:
                     torch.cuda.synchronize()
@@ -478,11 +483,20 @@ def run_b200(args):
                 else:
                     bs = buf.sample()
                     r_.update(bs[0], bs[2], bs[1], bs[3], bs[4], bs[5], bs[6], fuse_target=True, synced=True)
-                loss_host = float(nn_.last_critic_loss)          # device -> host read of the step's result
+                loss_pin[it & 1:(it & 1) + 1].copy_(nn_.last_critic_loss.reshape(1), non_blocking=True)
+                loss_ev[it & 1].record()
+                if it > 0:
+                    loss_ev[(it - 1) & 1].synchronize()
+                    loss_host = float(loss_pin[(it - 1) & 1])    # device -> host read of update it - 1
+                    n_read += 1
+            loss_ev[(3 + e2e_updates - 1) & 1].synchronize()
+            loss_host = float(loss_pin[(3 + e2e_updates - 1) & 1])
+            n_read += 1
+            assert n_read == 3 + e2e_updates
             e2e_s_ = max_over_ranks(time.perf_counter() - t0_)
             leg['e2e'] = {'value': e2e_updates / e2e_s_, 'unit': 'updates/s', 'h2d_bytes_per_step': 8 * B_local, 'd2h_bytes_per_step': 4,
                           'note': 'as RL_AC.learn_and_update runs it: ReplayBuffer.sample (host index draw + H2D + device gather into the graph inputs) + '
-                                  'the update replayed as a CUDA graph + loss read-back per update; '
+                                  'the update replayed as a CUDA graph + the loss of EVERY update read back (copy issued behind the update, waited for after the next one is launched); '
                                   f'last loss {loss_host:.4g}'}
         del r_, nn_
         return leg
