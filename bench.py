@@ -385,7 +385,7 @@ def run_b200(args):
 
     # ---- K3 Sobolev critic+actor updates/s (the second half of the metric): data resident, gradients summed across GPUs inside
     # the Adam kernels.  Legs: the reference's conf batch (64 per GPU, fp32-FMA tile kernels, latency-bound) and the BASELINE
-    # config 2 / 3 batches (4096, 16384: tcgen05 engine from B = 3072); UR5 (config 5) with its global batches split over the ranks.
+    # config 2 / 3 batches (4096, 16384: tcgen05 engine from B = 2400); UR5 (config 5) with its global batches split over the ranks.
     from cacto_b200.replay_buffer import ReplayBuffer
 
     def update_leg(system, B_local, n_eager, n_graph, e2e_updates=0):

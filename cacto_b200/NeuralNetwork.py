@@ -241,7 +241,9 @@ class NN:
     # -- gradient launches (shared by the eager methods below and by RL_AC's CUDA-graph update) -----------
     # Batch size from which the 'sine' critic / actor gradients run on the tensor-core kernels (csrc/update_tc.cu: 128-sample
     # tiles, one tile per SM) instead of the fused fp32-FMA tile kernels (csrc/update.cu).  ``update_engine``: 'auto' | 'fma' | 'tc'.
-    TC_MIN_BATCH = 3072
+    # Crossover measured as graph-replayed updates (profiles/README.md): the FMA engine's 16-row tiles fill one wave of the 148 SMs up to
+    # 2368 samples (190 us at 2048 vs 197 us on tensor cores) and need a second one beyond (245 vs 204 us at 2560).
+    TC_MIN_BATCH = 2400
     update_engine = 'auto'
 
     def _use_tc(self, B):
