@@ -31,6 +31,30 @@ __device__ __forceinline__ void read_sample(const T* __restrict__ g, int64_t B, 
     }
   }
 }
+// Two inputs of a sample (state and action) with ONE barrier pair: both tiles are requested back to back into disjoint parts of
+// the shared buffer (the step kernel moves 68 bytes per sample: a second load that only starts after the first has been waited
+// for and consumed doubles the exposed memory latency of a block).
+template <int W1, int W2, int NT, int LAYOUT, typename T>
+__device__ __forceinline__ void read_sample2(const T* __restrict__ g1, const T* __restrict__ g2, int64_t B, int64_t row0, int rows, T* smem,
+                                             T* out1, T* out2) {
+  if (LAYOUT == LAYOUT_ROWS) {
+    constexpr int WP1 = pad_odd(W1), WP2 = pad_odd(W2);
+    T* smem2 = smem + ((NT * WP1 * (int)sizeof(T) + 15) / 16) * 16 / (int)sizeof(T);
+    __syncthreads();
+    tile_load_rows<W1, NT, T>(g1 + row0 * W1, smem, rows);
+    tile_load_rows<W2, NT, T>(g2 + row0 * W2, smem2, rows);
+    __syncthreads();
+    if ((int)threadIdx.x < rows) {
+#pragma unroll
+      for (int c = 0; c < W1; ++c) out1[c] = smem[threadIdx.x * WP1 + c];
+#pragma unroll
+      for (int c = 0; c < W2; ++c) out2[c] = smem2[threadIdx.x * WP2 + c];
+    }
+  } else {
+    read_sample<W1, NT, LAYOUT, T>(g1, B, row0, rows, smem, out1);
+    read_sample<W2, NT, LAYOUT, T>(g2, B, row0, rows, smem, out2);
+  }
+}
 template <int W, int NT, int LAYOUT, typename T>
 __device__ __forceinline__ void write_sample(T* __restrict__ g, int64_t B, int64_t row0, int rows, T* smem, const T* vals) {
   if (LAYOUT == LAYOUT_ROWS) {
@@ -53,8 +77,7 @@ __global__ void __launch_bounds__(Tpb<SYS>::V) k_dyn_step(const __grid_constant_
   const int64_t row0 = (int64_t)blockIdx.x * NT;
   const int rows = (int)min((int64_t)NT, B - row0);
   T x[NS], u[NA], xn[NS];
-  read_sample<NS, NT, LAYOUT, T>(state, B, row0, rows, smem, x);
-  read_sample<NA, NT, LAYOUT, T>(action, B, row0, rows, smem, u);
+  read_sample2<NS, NA, NT, LAYOUT, T>(state, action, B, row0, rows, smem, x, u);
   if ((int)threadIdx.x < rows) {
     sys_step<SYS, T>(P, x, u, xn);
     xn[NX] = x[NX] + T(P.dt);
@@ -98,8 +121,7 @@ __global__ void __launch_bounds__(Tpb<SYS>::V) k_dyn_augmented(const __grid_cons
   const int64_t row0 = (int64_t)blockIdx.x * NT;
   const int rows = (int)min((int64_t)NT, B - row0);
   T x[NS], u[NA], Fx[NX * NX], Fu[NX * NA];
-  read_sample<NS, NT, LAYOUT, T>(state, B, row0, rows, smem, x);
-  read_sample<NA, NT, LAYOUT, T>(action, B, row0, rows, smem, u);
+  read_sample2<NS, NA, NT, LAYOUT, T>(state, action, B, row0, rows, smem, x, u);
   if ((int)threadIdx.x < rows) sys_jac<SYS, T>(P, x, u, Fx, Fu);
   write_sample<NX * NX, NT, LAYOUT, T>(Fx_out, B, row0, rows, smem, Fx);
   write_sample<NX * NA, NT, LAYOUT, T>(Fu_out, B, row0, rows, smem, Fu);
@@ -152,7 +174,8 @@ constexpr size_t tile_bytes() {
   constexpr int W1 = pad_odd(NX * NX), W2 = pad_odd((NX + 1) * NA);
   constexpr size_t w = (W1 > W2 ? W1 : W2);
   constexpr size_t a = w * Tpb<SYS>::V * sizeof(T), b = (size_t)9 * Tpb<SYS>::V * sizeof(double);
-  return a > b ? a : b;
+  constexpr size_t c = (size_t)(pad_odd(NX + 1) + pad_odd(NA)) * Tpb<SYS>::V * sizeof(T) + 16;       // state and action tiles side by side
+  return (a > b ? a : b) > c ? (a > b ? a : b) : c;
 }
 
 template <typename K>
