@@ -355,13 +355,29 @@ class RL_AC:
             rewards[:, bad] = rw
         return n
 
-    def rollout_to_host(self, ics_host, ep, states_host, controls_host, flags_host, mode='pipelined', engine=None, n_chunks=8):
+    class _PendingRollouts:
+        """Handle of ``rollout_to_host(..., wait=False)``: ``wait()`` blocks until the trajectories are in the host buffers
+        (and re-runs rollouts the fp16 engine flagged); ``horizon`` = NSTEPS_SH per rollout."""
+
+        def __init__(self, finish, horizon):
+            self._finish, self.horizon = finish, horizon
+
+        def wait(self):
+            if self._finish is not None:
+                self._finish()
+                self._finish = None
+            return self.horizon
+
+    def rollout_to_host(self, ics_host, ep, states_host, controls_host, flags_host, mode='pipelined', engine=None, n_chunks=8, wait=True):
         """Host-to-host rollouts for the TO feeder: ``ics_host`` [B, ns] fp64 (pinned) -> ``states_host``
         [T_max+1, ns, B], ``controls_host`` [T_max, na, B] fp64 and ``flags_host`` [B] int32 (pinned).
         mode 'pipelined' (default): the batch is rolled out in ``n_chunks`` sub-batches; while sub-batch k + 1 runs, the copy
         engine moves the trajectories of sub-batch k into their columns of the host buffers (strided DMA, ~55 GB/s).
         mode 'zero_copy': the kernel stores straight into the pinned host buffers over PCIe (UVA, ~48 GB/s).
-        mode 'staged': H2D, kernel into HBM, D2H."""
+        mode 'staged': H2D, kernel into HBM, D2H.
+        ``wait=False`` (pipelined mode): returns a handle right after the work is queued; a caller that alternates between two sets of
+        host buffers queues batch k + 1 before waiting for batch k, so that the first kernel and the host-side bookkeeping of a batch
+        overlap the tail of the previous batch's copies."""
         c = self.conf
         dev = _device()
         B = ics_host.shape[0]
@@ -381,7 +397,7 @@ class RL_AC:
                           f=[torch.empty(bc, dtype=torch.int32, device=dev) for _ in range(2)])
                 self._pipe_stage = st
             main, side = torch.cuda.current_stream(), st['copy_stream']
-            copied = [None, None]
+            copied = st.setdefault('copied', [None, None])         # (kept across calls: the staging slots are shared by batches in flight)
             for k, b0 in enumerate(range(0, B, bc)):
                 n = min(bc, B - b0)
                 slot = k & 1
@@ -400,6 +416,14 @@ class RL_AC:
                 check(lib.cacto_copy2d_to_host(flags_host.data_ptr() + 4 * b0, 4 * n, ptr(fk), 4 * n, 4 * n, 1, sp), 'copy2d')
                 copied[slot] = torch.cuda.Event()
                 copied[slot].record(side)
+            if not wait:
+                tail = torch.cuda.Event()
+                tail.record(side)
+
+                def finish():
+                    tail.synchronize()
+                    self._patch_flagged_host(ics_host, hz_np, ep, states_host, controls_host, flags_host, engine)
+                return self._PendingRollouts(finish, hz_np)
             side.synchronize()
         elif mode == 'zero_copy':
             flags = torch.empty(B, dtype=torch.int32, device=dev)
@@ -417,7 +441,11 @@ class RL_AC:
             controls_host.copy_(buf[1], non_blocking=True)
             flags_host.copy_(buf[2], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        # fp16-range failures of the 'tc' engines (see _retry_flagged): re-run on 'fma' and patch the host buffers
+        self._patch_flagged_host(ics_host, hz_np, ep, states_host, controls_host, flags_host, engine)
+        return hz_np if wait else self._PendingRollouts(None, hz_np)
+
+    def _patch_flagged_host(self, ics_host, hz_np, ep, states_host, controls_host, flags_host, engine):
+        """fp16-range failures of the 'tc' engines (see _retry_flagged): re-run on 'fma' and patch the host buffers."""
         if ep != 0 and (engine or self.rollout_engine) in ('tc', 'tc2') and (self.actor_model.ns <= 8 or self.ur5_on_tc16):
             bad = (flags_host == 0).nonzero().reshape(-1)
             if bad.numel() > 0:
@@ -425,7 +453,6 @@ class RL_AC:
                 states_host[:, :, bad] = r['states'].cpu()
                 controls_host[:, :, bad] = r['controls'].cpu()
                 flags_host[bad] = r['success'].cpu()
-        return hz_np
 
     def create_TO_init(self, ep, ICS):
         """RL.py:197-233 for one initial condition -> (ICS, init_TO_states[T+1, ns], init_TO_controls[T, na], T, success)."""

@@ -155,6 +155,40 @@ def test_rollout_to_host_modes_agree():
         assert np.abs(ct.numpy()[mc] - ref['controls'].cpu().numpy()[mc]).max() < 1e-5
 
 
+def test_rollout_to_host_without_waiting_delivers_the_same_batches():
+    """wait=False: two batches in flight on alternating host buffers (the staging slots on the device are shared): each arrives
+    complete and bit-identical to the blocking call."""
+    conf, env, rl = setup('manipulator')
+    B, T, ns, na = 700, conf.NSTEPS, conf.nb_state, conf.nb_action
+    ih = [torch.as_tensor(ics(conf, B, 21 + i)).pin_memory() for i in range(3)]
+    def bufs():
+        return (torch.full((T + 1, ns, B), float('nan'), dtype=torch.float64).pin_memory(),
+                torch.full((T, na, B), float('nan'), dtype=torch.float64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory())
+    want = []
+    for x in ih:
+        st, ct, fl = bufs()
+        hz = rl.rollout_to_host(x, 1, st, ct, fl, n_chunks=3)
+        want.append((st.clone(), ct.clone(), fl.clone(), hz))
+    sets = (bufs(), bufs())
+    pending, got = None, []
+    for k, x in enumerate(ih):
+        cur = sets[k & 1]
+        h = rl.rollout_to_host(x, 1, cur[0], cur[1], cur[2], n_chunks=3, wait=False)
+        if pending is not None:
+            hz = pending[0].wait()
+            got.append((pending[1][0].clone(), pending[1][1].clone(), pending[1][2].clone(), hz))
+        pending = (h, cur)
+    hz = pending[0].wait()
+    got.append((pending[1][0].clone(), pending[1][1].clone(), pending[1][2].clone(), hz))
+    for (st, ct, fl, hz), (st2, ct2, fl2, hz2) in zip(want, got):
+        assert (hz == hz2).all() and bool(fl2.all()) and torch.equal(fl, fl2)
+        knots = np.arange(T + 1)[:, None] <= hz[None, :]                   # entries past a rollout's horizon are left untouched
+        m = np.broadcast_to(knots[:, None, :], st.shape)
+        assert np.array_equal(st.numpy()[m], st2.numpy()[m])
+        mc = np.broadcast_to((np.arange(T)[:, None] < hz[None, :])[:, None, :], ct.shape)
+        assert np.array_equal(ct.numpy()[mc], ct2.numpy()[mc])
+
+
 def test_tc_engine_overflow_falls_back_to_fma():
     """An actor whose hidden activations leave the fp16 range of the 'tc' engine (rollout_tc16.cu: +-2047 after scaling) must not
     change the outcome: the reference aborts on NaN only (RL.py:229-231).  Flagged rollouts are re-run on 'fma'."""
