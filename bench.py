@@ -367,36 +367,44 @@ def run_b200(args):
     achieved_tflops = B * T * FLOPS_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e12
 
     # ---- e2e: host ICS (pinned) -> H2D -> rollout -> fp64 warm-start trajectories in pinned host memory
-    st_host = torch.empty((T + 1, ns, B), dtype=torch.float64).pin_memory()
-    ct_host = torch.empty((T, na, B), dtype=torch.float64).pin_memory()
-    fl_host = torch.empty(B, dtype=torch.int32).pin_memory()
-    # two sets of host buffers: batch k + 1 is queued before batch k is waited for (its first kernel and host-side bookkeeping overlap
-    # the tail of batch k's copies); every batch is waited for and checked inside the timed region
-    st_host2 = torch.empty((T + 1, ns, B), dtype=torch.float64).pin_memory()
-    ct_host2 = torch.empty((T, na, B), dtype=torch.float64).pin_memory()
-    fl_host2 = torch.empty(B, dtype=torch.int32).pin_memory()
-    host_sets = ((st_host, ct_host, fl_host), (st_host2, ct_host2, fl_host2))
-    for _ in range(max(1, W // 2)):
-        rl.rollout_to_host(ics_host, 1, st_host, ct_host, fl_host)
-        rl.rollout_to_host(ics_host, 1, st_host2, ct_host2, fl_host2)
-    barrier()
-    t0 = time.perf_counter()
-    pending, ok_all = None, True
-    for k in range(K):
-        hs = host_sets[k & 1]
-        nxt = rl.rollout_to_host(ics_host, 1, hs[0], hs[1], hs[2], wait=False)
-        if pending is not None:
-            pending[0].wait()
-            ok_all = ok_all and bool(pending[1].all())
-        pending = (nxt, hs[2])
-    pending[0].wait()
-    ok_all = ok_all and bool(pending[1].all())
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    assert ok_all
-    e2e_value = B * T * K * world / e2e_s
+    def e2e_leg(compact):
+        # two sets of host buffers: batch k + 1 is queued before batch k is waited for (its first kernel and host-side bookkeeping
+        # overlap the tail of batch k's copies); every batch is waited for and checked inside the timed region
+        def host_set():
+            if compact:
+                return (torch.empty((T + 1, ns - 1, B), dtype=torch.float64).pin_memory(),
+                        torch.empty((T, na, B), dtype=torch.float32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
+            return (torch.empty((T + 1, ns, B), dtype=torch.float64).pin_memory(),
+                    torch.empty((T, na, B), dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
+        host_sets = (host_set(), host_set())
+        for _ in range(max(1, W // 2)):
+            for hs in host_sets:
+                rl.rollout_to_host(ics_host, 1, hs[0], hs[1], hs[2], compact=compact)
+        barrier()
+        t0 = time.perf_counter()
+        pending, ok_all = None, True
+        for k in range(K):
+            hs = host_sets[k & 1]
+            nxt = rl.rollout_to_host(ics_host, 1, hs[0], hs[1], hs[2], wait=False, compact=compact)
+            if pending is not None:
+                pending[0].wait()
+                ok_all = ok_all and bool(pending[1].all())
+            pending = (nxt, hs[2])
+        pending[0].wait()
+        ok_all = ok_all and bool(pending[1].all())
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        assert ok_all
+        hs = host_sets[0]
+        d2h_bytes = hs[0].numel() * 8 + hs[1].numel() * hs[1].element_size() + hs[2].numel() * 4
+        del host_sets
+        return B * T * K * world / e2e_s, d2h_bytes
+
+    e2e_value, d2h = e2e_leg(False)
+    # the same batches in the compact transfer format (no time row, controls as the fp32 values the actor produced): bit-
+    # reconstructible on the host (RL.CompactRollouts, tests/test_gpu_rollout.py), 25 % fewer bytes over PCIe
+    e2e_compact_value, d2h_compact = e2e_leg(True)
     h2d = ics_host.numel() * 8 + B * 4
-    d2h = (st_host.numel() + ct_host.numel()) * 8 + fl_host.numel() * 4
 
     # ---- K3 Sobolev critic+actor updates/s (the second half of the metric): data resident, gradients summed across GPUs inside
     # the Adam kernels.  Legs: the reference's conf batch (64 per GPU, fp32-FMA tile kernels, latency-bound) and the BASELINE
@@ -620,7 +628,11 @@ def run_b200(args):
                             'PCIe-bound (1.06 GB per step)'},
             'gpu_launches': K * launches_per_step,          # device-resident leg; the e2e leg launches 2 + 8 kernels per step
             'clocks': clocks,
-            'extra': {'update': {'metric': 'Sobolev actor-critic updates/s (RL_AC.update: critic gradient, Adam + Polyak, actor gradient, Adam)',
+            'extra': {'e2e_compact': {'value': e2e_compact_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_compact,
+                                      'note': 'rollout_to_host(compact=True): the same batches without the time row (t_k = t_0 + k dt by repeated addition) and with '
+                                              'the controls as the fp32 values the actor produced; RL.CompactRollouts rebuilds the fp64 arrays bit-identically '
+                                              '(tests/test_gpu_rollout.py::test_rollout_to_host_compact_is_bit_reconstructible); not the headline e2e'},
+                      'update': {'metric': 'Sobolev actor-critic updates/s (RL_AC.update: critic gradient, Adam + Polyak, actor gradient, Adam)',
                                  'legs': upd_legs, 'dp_check': dp_check,
                                  'cpu_baseline': (cpu or {}).get('update'),
                                  'note': 'updates_per_s = CUDA-graph replay where capture is possible, else eager; value of a leg counts updates of '

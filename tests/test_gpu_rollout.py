@@ -189,6 +189,35 @@ def test_rollout_to_host_without_waiting_delivers_the_same_batches():
         assert np.array_equal(ct.numpy()[mc], ct2.numpy()[mc])
 
 
+def test_rollout_to_host_compact_is_bit_reconstructible():
+    """compact=True moves 25 % fewer bytes over PCIe (no time row, controls as the fp32 values the actor produced); the
+    reference-shaped arrays ``CompactRollouts`` rebuilds are bit-identical to the full-format transfer of the same batch."""
+    from cacto_b200.RL import CompactRollouts
+    conf, env, rl = setup('manipulator')
+    B, T, ns, na = 900, conf.NSTEPS, conf.nb_state, conf.nb_action
+    X0 = ics(conf, B, 31)
+    X0[:, -1] = np.random.default_rng(5).integers(0, T, B) * conf.dt          # ragged horizons, non-zero start times
+    ih = torch.as_tensor(X0).pin_memory()
+    st = torch.full((T + 1, ns, B), float('nan'), dtype=torch.float64).pin_memory()
+    ct = torch.full((T, na, B), float('nan'), dtype=torch.float64).pin_memory()
+    fl = torch.zeros(B, dtype=torch.int32).pin_memory()
+    hz = rl.rollout_to_host(ih, 1, st, ct, fl, n_chunks=3)
+    sc = torch.full((T + 1, ns - 1, B), float('nan'), dtype=torch.float64).pin_memory()
+    cc = torch.full((T, na, B), float('nan'), dtype=torch.float32).pin_memory()
+    fc = torch.zeros(B, dtype=torch.int32).pin_memory()
+    hzc = rl.rollout_to_host(ih, 1, sc, cc, fc, n_chunks=3, compact=True)
+    assert (hz == hzc).all() and bool(fc.all()) and torch.equal(fl, fc)
+    view = CompactRollouts(conf, ih, sc, cc, hzc)
+    for b in range(B):
+        Tb = int(hz[b])
+        assert np.array_equal(view.states(b), st.numpy()[:Tb + 1, :, b])
+        assert np.array_equal(view.controls(b), ct.numpy()[:Tb, :, b])
+    with pytest.raises(ValueError):
+        rl.rollout_to_host(ih, 1, st, ct, fl, compact=True)                    # full-format buffers with compact=True
+    with pytest.raises(ValueError):
+        rl.rollout_to_host(ih, 1, sc, cc, fc, mode='staged', compact=True)
+
+
 def test_tc_engine_overflow_falls_back_to_fma():
     """An actor whose hidden activations leave the fp16 range of the 'tc' engine (rollout_tc16.cu: +-2047 after scaling) must not
     change the outcome: the reference aborts on NaN only (RL.py:229-231).  Flagged rollouts are re-run on 'fma'."""
