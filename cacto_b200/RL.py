@@ -439,20 +439,18 @@ class RL_AC:
                 uk = st['u'][slot][:T_max * na * n].view(T_max, na, n)
                 fk = st['f'][slot][:n]
                 self._launch_rollout(ep, ics[b0:b0 + n], hz[b0:b0 + n], T_max, sk, uk, fk, None, n, engine, prepare=(k == 0))
-                if compact:                                        # drop the time row, narrow the controls (exact) before the copy
-                    if 'sc' not in st:
-                        st['sc'] = [torch.empty((T_max + 1) * (ns - 1) * bc, dtype=torch.float64, device=dev) for _ in range(2)]
+                if compact:                                        # narrow the controls (exact); the copy itself skips the time rows
+                    if 'uc' not in st:
                         st['uc'] = [torch.empty(T_max * na * bc, dtype=torch.float32, device=dev) for _ in range(2)]
-                    sc = st['sc'][slot][:(T_max + 1) * (ns - 1) * n].view(T_max + 1, ns - 1, n)
-                    uc = st['uc'][slot][:T_max * na * n].view(T_max, na, n)
-                    sc.copy_(sk[:, :ns - 1, :])
-                    uc.copy_(uk)
+                    uc = st['uc'][slot][:T_max * na * n]
+                    check(lib.cacto_narrow_f64_to_f32(ptr(uk), ptr(uc), T_max * na * n, main.cuda_stream), 'narrow')
                 done = torch.cuda.Event()
                 done.record(main)
                 side.wait_event(done)
                 sp = side.cuda_stream
                 if compact:
-                    check(lib.cacto_copy2d_to_host(states_host.data_ptr() + 8 * b0, 8 * B, ptr(sc), 8 * n, 8 * n, (T_max + 1) * (ns - 1), sp), 'copy2d')
+                    check(lib.cacto_copy3d_to_host(states_host.data_ptr() + 8 * b0, 8 * B, ns - 1, ptr(sk), 8 * n, ns, 8 * n, ns - 1, T_max + 1, sp),
+                          'copy3d')
                     check(lib.cacto_copy2d_to_host(controls_host.data_ptr() + 4 * b0, 4 * B, ptr(uc), 4 * n, 4 * n, T_max * na, sp), 'copy2d')
                 else:
                     check(lib.cacto_copy2d_to_host(states_host.data_ptr() + 8 * b0, 8 * B, ptr(sk), 8 * n, 8 * n, (T_max + 1) * ns, sp), 'copy2d')

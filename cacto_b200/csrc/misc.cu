@@ -18,6 +18,49 @@ extern "C" int cacto_copy2d_to_host(void* dst_host, int64_t dst_pitch, const voi
                                 cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 }
 
+// The same for a stack of column blocks: slab k of the source holds src_rows rows (pitch src_pitch), of which the first `rows`
+// go to slab k of the destination (dst_rows rows of pitch dst_pitch) -- one cudaMemcpy3DAsync.  The compact transfer format of
+// RL_AC.rollout_to_host drops the time row of every knot this way (rows = ns - 1 of src_rows = ns) without a staging pass.
+extern "C" int cacto_copy3d_to_host(void* dst_host, int64_t dst_pitch, int64_t dst_rows, const void* src_dev, int64_t src_pitch,
+                                    int64_t src_rows, int64_t width_bytes, int64_t rows, int64_t slabs, void* stream) {
+  if (!dst_host || !src_dev) return CACTO_E_ARG;
+  if (width_bytes < 0 || rows < 0 || slabs < 0 || dst_pitch < width_bytes || src_pitch < width_bytes || dst_rows < rows || src_rows < rows)
+    return CACTO_E_SIZE;
+  if (width_bytes == 0 || rows == 0 || slabs == 0) return 0;
+  cudaMemcpy3DParms c = {};
+  c.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src_dev), (size_t)src_pitch, (size_t)width_bytes, (size_t)src_rows);
+  c.dstPtr = make_cudaPitchedPtr(dst_host, (size_t)dst_pitch, (size_t)width_bytes, (size_t)dst_rows);
+  c.extent = make_cudaExtent((size_t)width_bytes, (size_t)rows, (size_t)slabs);
+  c.kind = cudaMemcpyDeviceToHost;
+  return (int)cudaMemcpy3DAsync(&c, (cudaStream_t)stream);
+}
+
+// fp64 -> fp32 of values that ARE fp32 numbers (the controls: fp32 actor outputs widened for the fp64 dynamics, RL.py:223): exact.
+// HBM-bound: 12 bytes per element, 32-byte loads / 16-byte stores.
+namespace cacto {
+__global__ void __launch_bounds__(256) k_narrow_f64(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const double2 a = reinterpret_cast<const double2*>(src)[2 * i], b = reinterpret_cast<const double2*>(src)[2 * i + 1];
+    reinterpret_cast<float4*>(dst)[i] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (float)src[i];
+}
+}  // namespace cacto
+
+extern "C" int cacto_narrow_f64_to_f32(const double* src, float* dst, int64_t n, void* stream) {
+  if (n < 0) return CACTO_E_SIZE;
+  if (n == 0) return 0;
+  if (!src || !dst || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return CACTO_E_ARG;
+  int64_t ctas = (n / 4 + 255) / 256;
+  if (ctas < 1) ctas = 1;
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  cacto::k_narrow_f64<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  CACTO_LAUNCH_CHECK();
+  return 0;
+}
+
 // p_i ** alpha on the HOST with the C library's pow -- the function CPython's float ** float calls, so the priorities written
 // into the trees carry the bits of the reference's `priority ** self._alpha` (replay_buffer.py:210-216); CUDA's pow is not
 // correctly rounded and would change them.  One call per batch instead of a Python loop over B floats (0.4 ms at B = 4096).

@@ -158,6 +158,12 @@ int cacto_backward_pass(const cacto_sys_params* p, const int64_t* offsets, int32
  *      column block, rows x width_bytes, on the copy engine. */
 int cacto_copy2d_to_host(void* dst_host, int64_t dst_pitch, const void* src_dev, int64_t src_pitch, int64_t width_bytes,
                          int64_t rows, void* stream);
+/*      The same for `slabs` stacked column blocks: slab k of the source has src_rows rows of which the first `rows` go to slab k of
+ *      the destination (dst_rows rows); and the exact fp64 -> fp32 narrowing of the controls (fp32 actor outputs widened for the
+ *      fp64 dynamics, RL.py:223).  Together: the compact transfer format of the warm-start hand-off (no time row, fp32 controls). */
+int cacto_copy3d_to_host(void* dst_host, int64_t dst_pitch, int64_t dst_rows, const void* src_dev, int64_t src_pitch, int64_t src_rows,
+                         int64_t width_bytes, int64_t rows, int64_t slabs, void* stream);
+int cacto_narrow_f64_to_f32(const double* src, float* dst, int64_t n, void* stream);
 
 /* ---- Generic dense networks: the critic variants of NeuralNetwork.py besides 'sine' (create_critic_elu :65-78,
  *      create_critic_sine_elu :80-93, create_critic_relu :110-128), or any stack of <= CACTO_MLP_MAX_LAYERS dense layers of
