@@ -109,6 +109,7 @@ _SIGNATURES = {
     'cacto_copy3d_to_host': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                        C.c_void_p]),
     'cacto_narrow_f64_to_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cacto_host_mt19937_random': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     'cacto_mlp_forward_generic': (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]),
     'cacto_critic_grad_generic': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_int] + [C.c_void_p] * 6 + [C.c_float] + [C.c_void_p] * 5 +
                                   [C.c_int64, C.c_void_p]),

@@ -61,6 +61,36 @@ extern "C" int cacto_narrow_f64_to_f32(const double* src, float* dst, int64_t n,
   return 0;
 }
 
+// n draws of Python's random.random() on the HOST from a copy of the interpreter's generator state (random.getstate(): 624 words
+// of MT19937 + position; CPython _randommodule.c: a = next32 >> 5, b = next32 >> 6, (a * 2^26 + b) / 2^53), state advanced in
+// place: the stratified PER sampler (replay_buffer.py:139-157) consumes B draws per round from that stream, and a Python-level
+// loop over 4096 calls costs more than the rest of the round.  Same stream, same bits (tests/test_host_random.py).
+static inline uint32_t mt_next(uint32_t* mt, uint32_t* pos) {
+  if (*pos >= 624u) {
+    for (int k = 0; k < 624; ++k) {
+      const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+      mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    *pos = 0;
+  }
+  uint32_t y = mt[(*pos)++];
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+extern "C" int cacto_host_mt19937_random(uint32_t* state625, double* out, int64_t n) {
+  if (n < 0) return CACTO_E_SIZE;
+  if (!state625 || (n > 0 && !out)) return CACTO_E_ARG;
+  if (state625[624] > 624u) return CACTO_E_ARG;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t a = mt_next(state625, state625 + 624) >> 5, b = mt_next(state625, state625 + 624) >> 6;
+    out[i] = (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+  }
+  return 0;
+}
+
 // p_i ** alpha on the HOST with the C library's pow -- the function CPython's float ** float calls, so the priorities written
 // into the trees carry the bits of the reference's `priority ** self._alpha` (replay_buffer.py:210-216); CUDA's pow is not
 // correctly rounded and would change them.  One call per batch instead of a Python loop over B floats (0.4 ms at B = 4096).

@@ -97,6 +97,20 @@ class ReplayBuffer(object):
         return s, r, s1, dv, d, term, weights, None
 
 
+def python_randoms(n):
+    """``[random.random() for _ in range(n)]`` (replay_buffer.py:142-147 draws one per stratum) as an array: same generator, same
+    bits, same state afterwards.  From 1024 draws on, the interpreter's MT19937 state is advanced by one C call
+    (``cacto_host_mt19937_random``) instead of n Python-level calls (B = 4096: the loop was a third of the PER round)."""
+    state = random.getstate()
+    if n < 1024 or state[0] != 3 or len(state[1]) != 625:
+        return np.array([random.random() for _ in range(n)])
+    buf = np.fromiter(state[1], dtype=np.uint32, count=625)
+    out = np.empty(n, dtype=np.float64)
+    check(lib.cacto_host_mt19937_random(buf.ctypes.data, out.ctypes.data, n), 'host_mt19937_random')
+    random.setstate((state[0], tuple(buf.tolist()), state[2]))
+    return out
+
+
 class PrioritizedReplayBuffer(ReplayBuffer):
     """replay_buffer.py:87-240."""
 
@@ -135,7 +149,7 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         live in ONE packed device block so that sample() brings them to the host with a single copy."""
         B = self.conf.BATCH_SIZE
         if uniforms is None:
-            uniforms = np.array([random.random() for _ in range(B)])
+            uniforms = python_randoms(B)
         dev = self.storage_mat.device
         u = torch.as_tensor(np.asarray(uniforms, dtype=np.float64)).to(dev, non_blocking=True)
         pk = getattr(self, '_pack', None)

@@ -165,6 +165,10 @@ int cacto_copy3d_to_host(void* dst_host, int64_t dst_pitch, int64_t dst_rows, co
                          int64_t width_bytes, int64_t rows, int64_t slabs, void* stream);
 int cacto_narrow_f64_to_f32(const double* src, float* dst, int64_t n, void* stream);
 
+/* ---- host helper of the PER sampler (replay_buffer.py:142-147: `random.random()` once per stratum): n draws from a copy of the
+ *      interpreter's MT19937 state (random.getstate()[1]: 624 words + position), advanced in place -- same stream, same bits. */
+int cacto_host_mt19937_random(uint32_t* state625, double* out, int64_t n);
+
 /* ---- Generic dense networks: the critic variants of NeuralNetwork.py besides 'sine' (create_critic_elu :65-78,
  *      create_critic_sine_elu :80-93, create_critic_relu :110-128), or any stack of <= CACTO_MLP_MAX_LAYERS dense layers of
  *      <= 256 units.  Parameter block in Keras order [W1 (in x out), b1, ...]; act[l] is the activation after layer l (the last
