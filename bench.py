@@ -34,8 +34,9 @@ F_DYN = 250                                        # flops of the planar-3R forw
 FLOPS_PER_ENV_STEP = 2 * P_ACTOR_MACS + F_DYN
 # dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel per launch at the default workload, from the committed
 # `ncu --set full` captures under profiles/ (None until an engine has been captured)
-TRAFFIC_BYTES = {'tc': 8869376 + 998446080, 'tf32': 8953600 + 998347520}
-TRAFFIC_SOURCE = {'tc': 'profiles/r1_rollout_tc16_ncu_raw.csv (ncu --set full capture of this command; not re-measured in-run)',
+TRAFFIC_BYTES = {'tc': 8695296 + 1001016000, 'tf32': 8953600 + 998347520}
+TRAFFIC_SOURCE = {'tc': 'profiles/r2_rollout_tc16_ncu_raw.csv (ncu --set full capture of the same launch at the end of round 2, profiles/scripts/prof_rollout.py; '
+                        'not re-measured in-run; algorithmic output 1.056 GB allocated, 1.00 GB written: rows past a horizon are not stored)',
                   'tf32': 'profiles/r1_rollout_tc_ncu_raw.csv (ncu --set full capture; not re-measured in-run)'}
 
 
