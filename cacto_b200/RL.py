@@ -194,6 +194,34 @@ class RL_AC:
         nn.launch_actor_grad(am, cm, io['state'], io['term'], inv_B, None, B)
         self._reduce_and_step(self.actor_optimizer, am, cm, prepared=True)
 
+    def _critic_step_static(self, io, schedule=True):
+        """Critic half of ``_update_static`` (schedule, gradient, Adam + Polyak) on the tensors of ``io``."""
+        c, nn = self.conf, self.NN
+        B = io['state'].shape[0]
+        cm, tc, am = self.critic_model, self.target_critic, self.actor_model
+        if schedule:
+            self.critic_optimizer.prepare(cm.params.device, zero=nn.last_critic_loss)
+        nn.launch_critic_grad(cm, tc, io['state'], io['state_next'], io['partial_rtg'], io['dVdx'], io['done'], io['weights'], 1.0 / float(B),
+                              io['rtg'], io['V'], io['V_target'], B)
+        if c.MC:
+            self._reduce_and_step(self.critic_optimizer, cm, am, prepared=True)
+        else:
+            self._reduce_and_step(self.critic_optimizer, cm, am, target=tc, tau=c.UPDATE_RATE, prepared=True)
+
+    def _actor_step_static(self, io, schedule=True):
+        """Actor half of ``_update_static`` (schedule, gradient through the -- already updated -- critic, Adam)."""
+        B = io['state'].shape[0]
+        am, cm = self.actor_model, self.critic_model
+        if schedule:
+            self.actor_optimizer.prepare(am.params.device)
+        self.NN.launch_actor_grad(am, cm, io['state'], io['term'], 1.0 / float(B), None, B)
+        self._reduce_and_step(self.actor_optimizer, am, cm, prepared=True)
+
+    def make_pipelined_update_graph(self, batch_size=None):
+        """``PipelinedUpdateGraph``: consecutive updates overlapped on one GPU (critic step of batch i beside the actor step of batch
+        i - 1; same results as the sequential order).  Single-GPU, fused 'sine' engine only."""
+        return PipelinedUpdateGraph(self, int(batch_size or self.conf.BATCH_SIZE))
+
     def make_update_graph(self, batch_size=None):
         """Capture update + update_target for a fixed batch size into a CUDA graph.  Returns an ``UpdateGraph`` whose
         ``io`` tensors (state, state_next, partial_rtg, dVdx, done, term, weights -> rtg, V, V_target) are filled by
@@ -580,3 +608,125 @@ class UpdateGraph:
         self.rl.critic_optimizer.iterations += 1
         self.rl.actor_optimizer.iterations += 1
         return self.io['rtg'], self.io['V'], self.io['V_target']
+
+
+class PipelinedUpdateGraph:
+    """Consecutive updates of RL_AC.update (RL.py:101-111) software-pipelined on one GPU.
+
+    ``compute_critic_grad`` never evaluates the actor (NeuralNetwork.py:150-178) and the actor step of update i only needs the critic
+    as update i left it (RL.py:104-109), so the actor step of update i and the critic GRADIENT of update i + 1 are independent: replay
+    i + 1 runs them side by side (two branches of one CUDA graph) and applies the critic's Adam step only once the actor gradient of
+    update i has read the critic.  Every kernel sees exactly the inputs it sees in the sequential order, so the weights after
+    ``flush()`` are those of the sequential updates; at the conf batches, where both gradient kernels are latency-bound chains on
+    32 of the 148 SMs, the period drops from the sum of the two chains to the longer one.
+
+    Use: ``buffer.sample(out=g.io)`` -> ``rtg, V, V_target = g.replay()`` -> ... -> ``g.flush()`` before the actor is read (rollouts,
+    checkpoints).  Two sets of input tensors alternate (``g.io`` is the set the next ``replay`` trains the critic on)."""
+
+    def __init__(self, rl, B):
+        self.rl, self.B = rl, B
+        c, nn = rl.conf, rl.NN
+        world = rl.dist.get_world_size() if rl.dist is not None else 1
+        if world != 1:
+            raise ValueError('PipelinedUpdateGraph is single-GPU: the peer-memory exchange assumes alternating critic / actor steps')
+        if rl.critic_model.kind != 'critic_sine' or nn._use_tc(B):
+            raise ValueError("PipelinedUpdateGraph needs the fused 'sine' engine (the tcgen05 engine shares one workspace between the two steps)")
+        dev = _device()
+        ns = c.nb_state
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        def make_io():
+            return dict(state=torch.zeros((B, ns), **f32), state_next=torch.zeros((B, ns), **f32), partial_rtg=torch.zeros((B, 1), **f32),
+                        dVdx=torch.zeros((B, ns), **f32), done=torch.zeros((B, 1), **f32), term=torch.zeros((B, 1), dtype=torch.float64, device=dev),
+                        weights=torch.ones((B, 1), **f32), rtg=torch.zeros((B, 1), **f32), V=torch.zeros((B, 1), **f32),
+                        V_target=torch.zeros((B, 1), **f32))
+        self.ios = (make_io(), make_io())
+        self.turn, self.pending = 0, None
+        nets = (rl.actor_model, rl.critic_model, rl.target_critic)
+        opts = (rl.critic_optimizer, rl.actor_optimizer)
+        for o, n in ((rl.critic_optimizer, rl.critic_model), (rl.actor_optimizer, rl.actor_model)):
+            o.moments(n)
+            o._device_state(dev)
+        torch.cuda.synchronize()
+        for n in nets:
+            n.grad.zero_()
+        # snapshot the training state, warm up on a side stream (lazy initialisation), capture, restore
+        snap = [(t, t.clone()) for n in nets for t in (n.params, n.params_T) if t is not None]
+        snap += [(t, t.clone()) for o in opts for st in o._state.values() for t in st]
+        snap += [(o._dev['step'], o._dev['step'].clone()) for o in opts]
+        its = [o.iterations for o in opts]
+        self._side = torch.cuda.Stream()
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
+            for io in self.ios:
+                rl._critic_step_static(io)
+                rl._actor_step_static(io)
+        torch.cuda.current_stream().wait_stream(warm)
+        torch.cuda.synchronize()
+
+        def capture(fn):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return g
+        self.critic_only = [capture(lambda io=io: rl._critic_step_static(io)) for io in self.ios]
+        self.actor_only = [capture(lambda io=io: rl._actor_step_static(io)) for io in self.ios]
+        self.steady = [capture(lambda p=p: self._steady(p)) for p in (0, 1)]
+        for t, old in snap:
+            t.copy_(old)
+        for o, it in zip(opts, its):
+            o.iterations = it
+        torch.cuda.synchronize()
+        for n in nets:
+            n.grad.zero_()
+        torch.cuda.synchronize()
+
+    def _steady(self, p):
+        """Critic step on ios[p] beside the actor step on ios[1 - p] (the previous batch); both schedules in one launch."""
+        rl, nn = self.rl, self.rl.NN
+        c = rl.conf
+        io_c, io_a = self.ios[p], self.ios[1 - p]
+        B = self.B
+        cm, tc, am = rl.critic_model, rl.target_critic, rl.actor_model
+        main, side = torch.cuda.current_stream(), self._side
+        type(rl.critic_optimizer).prepare_pair(rl.critic_optimizer, rl.actor_optimizer, cm.params.device, zero=nn.last_critic_loss)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            nn.launch_actor_grad(am, cm, io_a['state'], io_a['term'], 1.0 / float(B), None, B)
+            read = torch.cuda.Event()
+            read.record(side)                                    # the previous critic has been read: its Adam step may go ahead
+            rl._reduce_and_step(rl.actor_optimizer, am, cm, prepared=True)
+        nn.launch_critic_grad(cm, tc, io_c['state'], io_c['state_next'], io_c['partial_rtg'], io_c['dVdx'], io_c['done'], io_c['weights'],
+                              1.0 / float(B), io_c['rtg'], io_c['V'], io_c['V_target'], B)
+        main.wait_event(read)
+        if c.MC:
+            rl._reduce_and_step(rl.critic_optimizer, cm, am, prepared=True)
+        else:
+            rl._reduce_and_step(rl.critic_optimizer, cm, am, target=tc, tau=c.UPDATE_RATE, prepared=True)
+        main.wait_stream(side)
+
+    @property
+    def io(self):
+        return self.ios[self.turn]
+
+    def replay(self):
+        """Critic step on the batch in ``io`` (and the outstanding actor step of the previous batch); returns that batch's
+        (rtg, V, V_target) tensors, valid until the replay after next."""
+        p = self.turn
+        if self.pending is None:
+            self.critic_only[p].replay()
+        else:
+            self.steady[p].replay()
+            self.rl.actor_optimizer.iterations += 1
+        self.rl.critic_optimizer.iterations += 1
+        self.pending, self.turn = p, 1 - p
+        io = self.ios[p]
+        return io['rtg'], io['V'], io['V_target']
+
+    def flush(self):
+        """Run the outstanding actor step: afterwards actor, critic and target are those of the sequential updates."""
+        if self.pending is not None:
+            self.actor_only[self.pending].replay()
+            self.rl.actor_optimizer.iterations += 1
+            self.pending = None

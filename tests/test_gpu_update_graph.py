@@ -86,3 +86,45 @@ def test_learn_and_update_runs_with_both_buffers(alpha):
     assert all(np.isfinite(w).all() for w in weights_of(rl))
     if alpha:
         assert buf._max_priority >= 1.0 and buf.exp_counter.sum() > 0
+
+
+@pytest.mark.parametrize('system,lr_schedule', [('manipulator', 1), ('car', 0), ('ur5', 0)])
+def test_pipelined_updates_equal_sequential_updates(system, lr_schedule):
+    """RL.PipelinedUpdateGraph: the actor step of update i runs beside the critic gradient of update i + 1 (they are independent,
+    NeuralNetwork.py:150-178 / RL.py:104-109); after flush() the weights are those of the sequential graph, and every replay
+    returns the critic outputs of its own batch."""
+    from cacto_b200.replay_buffer import ReplayBuffer
+    conf, rl_s = build(system, LR_SCHEDULE=lr_schedule)
+    _, rl_p = build(system, LR_SCHEDULE=lr_schedule)
+    buf = ReplayBuffer(conf)
+    fill(buf, conf, 5000)
+    before = weights_of(rl_p)
+    gs, gp = rl_s.make_update_graph(), rl_p.make_pipelined_update_graph()
+    for a, b in zip(before, weights_of(rl_p)):                 # capture must leave the training state untouched
+        np.testing.assert_array_equal(a, b)
+    assert rl_p.critic_optimizer.iterations == 0 and int(rl_p.actor_optimizer._dev['step'][0]) == 0
+    n = 7
+    for it in range(n):
+        idx = np.random.default_rng(it).integers(0, 5000, conf.BATCH_SIZE)
+        buf.sample(idx, out=gs.io)
+        rtg_s, V_s, _ = gs.replay()
+        buf.sample(idx, out=gp.io)
+        rtg_p, V_p, _ = gp.replay()
+        torch.testing.assert_close(rtg_p, rtg_s, rtol=2e-5, atol=2e-6)
+        torch.testing.assert_close(V_p, V_s, rtol=2e-5, atol=2e-6)
+        if it == 3:                                            # a flush in the middle (checkpoint): the pipeline restarts
+            gp.flush()
+            for a, b in zip(weights_of(rl_s), weights_of(rl_p)):
+                assert np.abs(a - b).max() <= 2e-5 * max(np.abs(a).max(), 1e-3)
+    assert rl_p.actor_optimizer.iterations == n - 1            # the last actor step is outstanding
+    gp.flush()
+    assert rl_p.critic_optimizer.iterations == rl_p.actor_optimizer.iterations == n
+    assert int(rl_p.actor_optimizer._dev['step'][0]) == n and int(rl_p.critic_optimizer._dev['step'][0]) == n
+    for a, b in zip(weights_of(rl_s), weights_of(rl_p)):
+        assert np.abs(a - b).max() <= 2e-5 * max(np.abs(a).max(), 1e-3)
+
+
+def test_pipelined_update_graph_refuses_what_it_cannot_overlap():
+    conf, rl = build(BATCH_SIZE=4096)
+    with pytest.raises(ValueError):
+        rl.make_pipelined_update_graph()                       # tcgen05 engine: one workspace shared by the two steps
