@@ -450,14 +450,39 @@ def run_b200(args):
                 del ug
             except Exception as exc:           # report, do not hide
                 graph_us = f'failed: {type(exc).__name__}: {exc}'
+        # one GPU, fused engine: consecutive updates software-pipelined (RL.PipelinedUpdateGraph, learn_and_update's default there):
+        # the actor step of update i beside the critic gradient of update i + 1, same weights as the sequential order
+        pipe_us = None
+        can_pipeline = world == 1 and r_.critic_model.kind == 'critic_sine' and not nn_._use_tc(B_local)
+        if can_pipeline:
+            try:
+                pg = r_.make_pipelined_update_graph(B_local)
+                for io_ in pg.ios:
+                    for k_, t_ in (('state', s_), ('state_next', sn_), ('partial_rtg', pr_), ('dVdx', dv_), ('done', d_), ('term', term_), ('weights', w_)):
+                        io_[k_].copy_(t_)
+                for _ in range(10):
+                    pg.replay()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(stream)
+                for _ in range(n_graph):
+                    pg.replay()
+                pg.flush()
+                b_.record(stream)
+                torch.cuda.synchronize()
+                pipe_us = a_.elapsed_time(b_) * 1e3 / n_graph
+                del pg
+            except Exception as exc:           # report, do not hide
+                pipe_us = f'failed: {type(exc).__name__}: {exc}'
         best_us = graph_us if isinstance(graph_us, float) else eager_us
+        if isinstance(pipe_us, float):
+            best_us = min(best_us, pipe_us)
         ns_, na_ = cf.nb_state, cf.nb_action
         P_c, P_a = 64 * ns_ + 28800, 256 * ns_ + 65536 + 256 * na_
         flops = 2.0 * B_local * (10 * P_c + 3 * P_a)                 # MACs ~ B (10 P_c + 3 P_a)
         ach = flops / (best_us * 1e-6) / 1e12
         tc = nn_._use_tc(B_local)
         leg = {'system': system, 'batch_per_gpu': B_local, 'global_batch': B_local * world, 'engine': 'tcgen05 (update_tc.cu)' if tc else 'fp32 FMA (update.cu)',
-               'us_per_update_eager': eager_us, 'us_per_update_cuda_graph': graph_us, 'updates_per_s': 1e6 / best_us,
+               'us_per_update_eager': eager_us, 'us_per_update_cuda_graph': graph_us, 'us_per_update_pipelined_graph': pipe_us, 'updates_per_s': 1e6 / best_us,
                'samples_per_s': B_local * world * 1e6 / best_us, 'algorithmic_flops_per_update': flops}
         if tc:
             leg['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': bf16_peak, 'unit': 'TFLOP/s', 'frac': ach / bf16_peak,
@@ -487,8 +512,8 @@ def run_b200(args):
             np.random.seed(0)
             ug_ = None
             if world == 1 or r_._peer is not None:
-                try:
-                    ug_ = r_.make_update_graph(B_local)          # learn_and_update's default: the update replayed as a CUDA graph
+                try:                                             # learn_and_update's defaults: the update replayed as a CUDA graph,
+                    ug_ = r_.make_pipelined_update_graph(B_local) if can_pipeline else r_.make_update_graph(B_local)   # pipelined on one GPU
                 except Exception:
                     ug_ = None
             r_.peer_barrier()
@@ -513,6 +538,9 @@ def run_b200(args):
                     loss_ev[(it - 1) & 1].synchronize()
                     loss_host = float(loss_pin[(it - 1) & 1])    # device -> host read of update it - 1
                     n_read += 1
+            if hasattr(ug_, 'flush'):
+                ug_.flush()                                      # the outstanding actor step of the pipelined graph
+                torch.cuda.synchronize()
             loss_ev[(3 + e2e_updates - 1) & 1].synchronize()
             loss_host = float(loss_pin[(3 + e2e_updates - 1) & 1])
             n_read += 1
@@ -520,7 +548,7 @@ def run_b200(args):
             e2e_s_ = max_over_ranks(time.perf_counter() - t0_)
             leg['e2e'] = {'value': e2e_updates / e2e_s_, 'unit': 'updates/s', 'h2d_bytes_per_step': 8 * B_local, 'd2h_bytes_per_step': 4,
                           'note': 'as RL_AC.learn_and_update runs it: ReplayBuffer.sample (host index draw + H2D + device gather into the graph inputs) + '
-                                  'the update replayed as a CUDA graph + the loss of EVERY update read back (copy issued behind the update, waited for after the next one is launched); '
+                                  'the update replayed as a CUDA graph (' + ('software-pipelined over consecutive updates, RL.PipelinedUpdateGraph' if hasattr(ug_, 'flush') else 'sequential') + ') + the loss of EVERY update read back (copy issued behind the update, waited for after the next one is launched); '
                                   f'last loss {loss_host:.4g}'}
         del r_, nn_
         return leg
@@ -543,6 +571,8 @@ def run_b200(args):
     updates_per_s = 1e6 / upd_legs[0]['us_per_update_eager']
     graph_us0 = upd_legs[0]['us_per_update_cuda_graph']
     graph_updates_per_s = 1e6 / graph_us0 if isinstance(graph_us0, float) else graph_us0
+    pipe_us0 = upd_legs[0].get('us_per_update_pipelined_graph')
+    pipelined_updates_per_s = 1e6 / pipe_us0 if isinstance(pipe_us0, float) else pipe_us0
 
     # data-parallel correctness, visible to the driver: one update from identical weights through the NVLink peer-memory exchange and
     # through NCCL all-reduces must agree (1e-4, the parity gate), and the replicas must stay bit-identical
@@ -643,6 +673,7 @@ def run_b200(args):
                                 'backward pass; UNPINNED for pinocchio-backed dynamics and tensorflow update semantics (absent here): '
                                 'tests/golden/make_golden_ext.py is the kit that pins them where the wheels exist',
                       'sobolev_updates_per_s': updates_per_s, 'sobolev_updates_per_s_cuda_graph': graph_updates_per_s,
+                      'sobolev_updates_per_s_pipelined_graph': pipelined_updates_per_s,   # one GPU: RL.PipelinedUpdateGraph (None with more ranks)
                       'update_batch_per_gpu': Bu, 'update_global_batch': Bu * world, 'update_kernels_per_update': 5,      # schedules (one launch for both optimizers), critic gradient, Adam + Polyak, actor gradient, Adam
                       
                       'update_gradient_exchange': ('none (1 GPU)' if world == 1 else

@@ -128,3 +128,27 @@ def test_pipelined_update_graph_refuses_what_it_cannot_overlap():
     conf, rl = build(BATCH_SIZE=4096)
     with pytest.raises(ValueError):
         rl.make_pipelined_update_graph()                       # tcgen05 engine: one workspace shared by the two steps
+
+
+@pytest.mark.parametrize('alpha', [0, 0.6])
+def test_learn_and_update_pipelined_by_default_matches_the_sequential_graph(alpha):
+    """learn_and_update on one GPU replays the pipelined graph (default); same index draws -> same weights as with
+    use_pipelined_updates = False, PER priorities included (they come from the critic outputs of each batch), checkpoints flushed."""
+    from cacto_b200.RL import PipelinedUpdateGraph, UpdateGraph
+    from cacto_b200.replay_buffer import PrioritizedReplayBuffer, ReplayBuffer
+    out = {}
+    for pipelined in (True, False):
+        conf, rl = build(prioritized_replay_alpha=alpha, UPDATE_LOOPS=np.array([9]), save_interval=10 ** 9)
+        rl.use_pipelined_updates = pipelined
+        buf = PrioritizedReplayBuffer(conf) if alpha else ReplayBuffer(conf)
+        fill(buf, conf, 3000)
+        random.seed(0)
+        np.random.seed(0)
+        cnt = rl.learn_and_update(0, buf, 0)
+        assert cnt == 9 and rl.actor_optimizer.iterations == rl.critic_optimizer.iterations == 9
+        assert isinstance(rl.update_graph, PipelinedUpdateGraph if pipelined else UpdateGraph) and getattr(rl.update_graph, 'pending', None) is None
+        out[pipelined] = (weights_of(rl), buf._it_sum._value.cpu().numpy().copy() if alpha else None)
+    for a, b in zip(out[True][0], out[False][0]):
+        assert np.abs(a - b).max() <= 1e-4 * max(np.abs(a).max(), 1e-3)
+    if alpha:
+        np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-4, atol=1e-9)
