@@ -87,14 +87,29 @@ class ReplayBuffer(object):
         unseeded ``np.random``: quirk Q5); ``out`` = pre-allocated tensors to fill (RL.UpdateGraph.io)."""
         if idxes is None:
             idxes = np.random.randint(0, self._max_idx(), size=self.conf.BATCH_SIZE)
-        idx_dev = torch.as_tensor(np.asarray(idxes, dtype=np.int64)).to(self.storage_mat.device, non_blocking=True)
+        if isinstance(idxes, torch.Tensor) and idxes.is_cuda:        # a row of draw_indices(): already on the device
+            idx_dev = idxes
+        else:
+            idx_dev = torch.as_tensor(np.asarray(idxes, dtype=np.int64)).to(self.storage_mat.device, non_blocking=True)
         s, r, s1, dv, d, term = self._gather(idx_dev, out)
         if out is not None:
-            out['weights'].fill_(1.0)
+            w_ = out['weights']                                      # importance weights of the uniform buffer: ones, written once --
+            if out.get('_ones_version') != w_._version:              # again only if something wrote into the tensor since (version counter)
+                w_.fill_(1.0)
+                out['_ones_version'] = w_._version
             weights = out['weights']
         else:
             weights = torch.ones((idx_dev.numel(), 1), dtype=torch.float32, device=s.device)
         return s, r, s1, dv, d, term, weights, None
+
+
+    def draw_indices(self, n_batches):
+        """The index draws of ``n_batches`` consecutive ``sample()`` calls (replay_buffer.py:45) as ONE ``np.random.randint`` call and
+        one host-to-device copy: int64 [n_batches, BATCH_SIZE] on the device, row k = what the k-th ``sample()`` would have drawn
+        (same values, same generator state afterwards: the legacy generator fills a request element by element;
+        tests/test_host_random.py).  Pass row k as ``sample(idxes=rows[k], out=...)``.  The buffer must not change in between."""
+        idx = np.random.randint(0, self._max_idx(), size=(int(n_batches), int(self.conf.BATCH_SIZE)))
+        return torch.as_tensor(np.asarray(idx, dtype=np.int64)).to(self.storage_mat.device, non_blocking=True)
 
 
 def python_randoms(n):
@@ -130,6 +145,10 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         dev = self.storage_mat.device
         self._stamp = torch.full((it_capacity,), -1, dtype=torch.int32, device=dev)
         self._totals = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def draw_indices(self, n_batches):
+        """Prioritized draws depend on the priorities the previous update wrote: nothing to draw ahead."""
+        return None
 
     def _tree_update(self, idx, val):
         dev = self.storage_mat.device

@@ -152,3 +152,47 @@ def test_learn_and_update_pipelined_by_default_matches_the_sequential_graph(alph
         assert np.abs(a - b).max() <= 1e-4 * max(np.abs(a).max(), 1e-3)
     if alpha:
         np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-4, atol=1e-9)
+
+
+def test_draw_indices_rows_are_the_draws_of_consecutive_samples():
+    from cacto_b200.replay_buffer import PrioritizedReplayBuffer, ReplayBuffer
+    conf, rl = build()
+    buf = ReplayBuffer(conf)
+    fill(buf, conf, 3000)
+    np.random.seed(3)
+    rows = buf.draw_indices(5)
+    state = np.random.get_state()
+    np.random.seed(3)
+    for k in range(5):
+        want = np.random.randint(0, buf._max_idx(), size=conf.BATCH_SIZE)
+        assert np.array_equal(rows[k].cpu().numpy(), want)
+        a, b = buf.sample(rows[k]), buf.sample(want)
+        for x, y in zip(a[:7], b[:7]):
+            assert torch.equal(x, y)
+    assert all(np.array_equal(x, y) if isinstance(x, np.ndarray) else x == y for x, y in zip(state, np.random.get_state()))
+    assert PrioritizedReplayBuffer(conf).draw_indices(5) is None
+    # graph inputs: the ones of the uniform buffer are written once, and again after anything else wrote into the tensor
+    g = rl.make_update_graph()
+    buf.sample(rows[0], out=g.io)
+    assert bool((g.io['weights'] == 1).all())
+    g.io['weights'].mul_(0.5)
+    buf.sample(rows[1], out=g.io)
+    assert bool((g.io['weights'] == 1).all())
+
+
+def test_learn_and_update_graph_path_draws_the_same_indices_as_the_eager_loop():
+    """learn_and_update draws the indices of its whole loop in one call when it replays a graph: same np.random stream as the
+    per-update draws of the eager loop (reference replay_buffer.py:45), hence the same training."""
+    from cacto_b200.replay_buffer import ReplayBuffer
+    out = {}
+    for graph in (True, False):
+        conf, rl = build(UPDATE_LOOPS=np.array([6]), save_interval=10 ** 9)
+        rl.use_update_graph = graph
+        buf = ReplayBuffer(conf)
+        fill(buf, conf, 3000)
+        np.random.seed(11)
+        assert rl.learn_and_update(0, buf, 0) == 6
+        out[graph] = (weights_of(rl), np.random.get_state()[1].copy())
+    assert np.array_equal(out[True][1], out[False][1])
+    for a, b in zip(out[True][0], out[False][0]):
+        assert np.abs(a - b).max() <= 1e-4 * max(np.abs(a).max(), 1e-3)

@@ -34,3 +34,18 @@ def test_python_randoms_keep_a_pending_gaussian():
     random.setstate(st)
     b = list(python_randoms(2048)) + [random.gauss(0, 1)]
     assert a == b
+
+
+@pytest.mark.parametrize('max_idx', [1, 3000, 65536, 65537, 2 ** 31 + 5])
+@pytest.mark.parametrize('B,K', [(64, 37), (1, 5), (4096, 3)])
+def test_one_randint_call_equals_consecutive_sample_draws(max_idx, B, K):
+    """ReplayBuffer.draw_indices relies on it: K calls of np.random.randint(0, n, B) (reference replay_buffer.py:45) and one call of
+    size (K, B) give the same numbers and leave the same generator state."""
+    np.random.seed(5)
+    a = np.stack([np.random.randint(0, max_idx, size=B) for _ in range(K)])
+    sa = np.random.get_state()
+    np.random.seed(5)
+    b = np.random.randint(0, max_idx, size=(K, B))
+    sb = np.random.get_state()
+    assert np.array_equal(a, b)
+    assert all(np.array_equal(x, y) if isinstance(x, np.ndarray) else x == y for x, y in zip(sa, sb))
