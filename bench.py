@@ -522,15 +522,15 @@ def run_b200(args):
             loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
             loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
             loss_host, n_read = float('nan'), 0
-            rows_ = buf.draw_indices(3) if ug_ is not None else None
+            rows_ = buf.index_stream(3) if ug_ is not None else None
             for it in range(3 + e2e_updates):
                 if it == 3:
                     torch.cuda.synchronize()
                     t0_ = time.perf_counter()
                     if ug_ is not None:                          # inside the timed region, as learn_and_update does it: the index draws
-                        rows_t = buf.draw_indices(e2e_updates)                     # of the whole loop in one np.random call + one copy
+                        rows_ = buf.index_stream(e2e_updates)                      # of the loop in chunks (ReplayBuffer.index_stream)
                 if ug_ is not None:
-                    buf.sample(rows_[it] if it < 3 else rows_t[it - 3], out=ug_.io)
+                    buf.sample(next(rows_), out=ug_.io)
                     ug_.replay()
                 else:
                     bs = buf.sample()
@@ -550,7 +550,7 @@ def run_b200(args):
             assert n_read == 3 + e2e_updates
             e2e_s_ = max_over_ranks(time.perf_counter() - t0_)
             leg['e2e'] = {'value': e2e_updates / e2e_s_, 'unit': 'updates/s', 'h2d_bytes_per_step': 8 * B_local, 'd2h_bytes_per_step': 4,
-                          'note': 'as RL_AC.learn_and_update runs it: the index draws of the loop in one np.random call + one H2D (ReplayBuffer.draw_indices: same stream), per update a device gather into the graph inputs + '
+                          'note': 'as RL_AC.learn_and_update runs it: the index draws of the loop in chunks of ~32 k indices, one np.random call + one H2D each (ReplayBuffer.index_stream: same stream), per update a device gather into the graph inputs + '
                                   'the update replayed as a CUDA graph (' + ('software-pipelined over consecutive updates, RL.PipelinedUpdateGraph' if hasattr(ug_, 'flush') else 'sequential') + ') + the loss of EVERY update read back (copy issued behind the update, waited for after the next one is launched); '
                                   f'last loss {loss_host:.4g}'}
         del r_, nn_

@@ -254,11 +254,11 @@ class RL_AC:
             graph = self.update_graph = make()
         flush = getattr(graph, 'flush', None)
         loops = int(self.conf.UPDATE_LOOPS[ep])
-        # uniform buffer: the index draws of the whole loop in one np.random call and one copy (same stream, ReplayBuffer.draw_indices)
-        rows = buffer.draw_indices(loops) if graph is not None and loops > 0 and hasattr(buffer, 'draw_indices') else None
+        # uniform buffer: the index draws of the loop in a few np.random calls and copies (same stream, ReplayBuffer.index_stream)
+        rows = buffer.index_stream(loops) if graph is not None and hasattr(buffer, 'index_stream') else iter(lambda: None, 0)
         for k in range(loops):
             if graph is not None:                       # captured update: the sampled rows land in the graph's input tensors
-                batch_idxes = buffer.sample(rows[k] if rows is not None else None, out=graph.io)[7]
+                batch_idxes = buffer.sample(next(rows), out=graph.io)[7]
                 reward_to_go_batch, critic_value, target_critic_value = graph.replay()
             else:
                 state_batch, partial_reward_to_go_batch, state_next_rollout_batch, dVdx_batch, d_batch, term_batch, weights_batch, batch_idxes = buffer.sample()

@@ -171,6 +171,11 @@ def test_draw_indices_rows_are_the_draws_of_consecutive_samples():
             assert torch.equal(x, y)
     assert all(np.array_equal(x, y) if isinstance(x, np.ndarray) else x == y for x, y in zip(state, np.random.get_state()))
     assert PrioritizedReplayBuffer(conf).draw_indices(5) is None
+    assert list(PrioritizedReplayBuffer(conf).index_stream(3)) == [None, None, None]
+    np.random.seed(3)                                          # the chunked stream: same rows, whatever the chunk size
+    got = [r.cpu().numpy() for r in buf.index_stream(5, chunk_indices=2 * conf.BATCH_SIZE)]
+    assert len(got) == 5 and all(np.array_equal(g_, rows[k].cpu().numpy()) for k, g_ in enumerate(got))
+    assert all(np.array_equal(x, y) if isinstance(x, np.ndarray) else x == y for x, y in zip(state, np.random.get_state()))
     # graph inputs: the ones of the uniform buffer are written once, and again after anything else wrote into the tensor
     g = rl.make_update_graph()
     buf.sample(rows[0], out=g.io)
