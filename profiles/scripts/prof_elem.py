@@ -1,4 +1,4 @@
-"""One launch of each element-wise kernel (manipulator, B = 4 Mi samples) for ncu: python scratch/prof_elem.py"""
+"""One launch of each element-wise kernel (manipulator, B = 4 Mi samples) for ncu: python profiles/scripts/prof_elem.py"""
 import sys; sys.path.insert(0, '/root/repo')
 import torch
 from cacto_b200.conf import get_conf

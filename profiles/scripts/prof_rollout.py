@@ -1,4 +1,4 @@
-"""One bench-size rollout launch per engine for ncu: python scratch/prof_rollout.py [engine] [B]"""
+"""One bench-size rollout launch per engine for ncu: python profiles/scripts/prof_rollout.py [engine] [B]"""
 import sys; sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from cacto_b200.conf import get_conf

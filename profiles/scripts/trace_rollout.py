@@ -1,4 +1,4 @@
-"""Event timeline of CTA 0 of k_rollout_tc16 (debug build with -DT16_TRACE): python scratch/trace_rollout.py"""
+"""Event timeline of CTA 0 of k_rollout_tc16 (debug build with -DT16_TRACE): python profiles/scripts/trace_rollout.py"""
 import os, sys, ctypes; sys.path.insert(0, '/root/repo')
 os.environ['CACTO_B200_LIB'] = '/root/repo/scratch/libcacto_trace.so'
 import numpy as np, torch
