@@ -88,14 +88,14 @@ def test_learn_and_update_runs_with_both_buffers(alpha):
         assert buf._max_priority >= 1.0 and buf.exp_counter.sum() > 0
 
 
-@pytest.mark.parametrize('system,lr_schedule', [('manipulator', 1), ('car', 0), ('ur5', 0)])
-def test_pipelined_updates_equal_sequential_updates(system, lr_schedule):
+@pytest.mark.parametrize('system,lr_schedule,mc', [('manipulator', 1, 0), ('car', 0, 0), ('ur5', 0, 0), ('manipulator', 0, 1)])
+def test_pipelined_updates_equal_sequential_updates(system, lr_schedule, mc):
     """RL.PipelinedUpdateGraph: the actor step of update i runs beside the critic gradient of update i + 1 (they are independent,
     NeuralNetwork.py:150-178 / RL.py:104-109); after flush() the weights are those of the sequential graph, and every replay
     returns the critic outputs of its own batch."""
     from cacto_b200.replay_buffer import ReplayBuffer
-    conf, rl_s = build(system, LR_SCHEDULE=lr_schedule)
-    _, rl_p = build(system, LR_SCHEDULE=lr_schedule)
+    conf, rl_s = build(system, LR_SCHEDULE=lr_schedule, MC=mc)         # MC = 1: no target network in the loss, no Polyak step
+    _, rl_p = build(system, LR_SCHEDULE=lr_schedule, MC=mc)
     buf = ReplayBuffer(conf)
     fill(buf, conf, 5000)
     before = weights_of(rl_p)
